@@ -41,6 +41,61 @@
 #include <string>
 #include <vector>
 
+// -----------------------------------------------------------------------------
+// Transcendental functions.  Two builds of this file (oracle/Makefile):
+//   libhelp3o_oracle.so        (default) the deterministic functions of
+//       pyhelp_b200/csrc/help_math.h -- REAL*4 intrinsics correctly rounded,
+//       REAL*8 intrinsics < 1 ulp, identical bits on CPU and GPU.  This is the
+//       build the GPU engine is compared with bit for bit.
+//   libhelp3o_oracle_glibc.so  (-DHELP_ORACLE_GLIBC) the host's libm, i.e. what a
+//       gfortran build of the reference links (powf/expf/pow ...).  Used to
+//       measure how far HELP's results move when only the last bit of libm
+//       moves (tests/test_libm_sensitivity.py, DESIGN.md "Numerics").
+// Both builds are pinned against the RCRA golden case.
+// -----------------------------------------------------------------------------
+#ifdef HELP_ORACLE_GLIBC
+#define R4_EXP(x) expf(x)
+#define R4_LOG(x) logf(x)
+#define R4_LOG10(x) log10f(x)
+#define R4_SIN(x) sinf(x)
+#define R4_COS(x) cosf(x)
+#define R4_TAN(x) tanf(x)
+#define R4_ACOS(x) acosf(x)
+#define R4_POW(x, y) powf(x, y)
+#define R4_SQRT(x) powf(x, 0.5f)
+#define R4_SQRTF(x) sqrtf(x)
+#define R4_POW8(x) powf(x, 8.f)
+#define R4_POW7(x) powf(x, 7.f)
+#define R4_POW4(x) powf(x, 4.f)
+#define R8_POW(x, y) pow(x, y)
+#define R8_LOG(x) log(x)
+#define R8_ATAN(x) atan(x)
+#define R8_SIN(x) sin(x)
+#define R8_COS(x) cos(x)
+#define R8_SQRT(x) sqrt(x)
+#else
+#include "../pyhelp_b200/csrc/help_math.h"
+#define R4_EXP(x) helpmath::r4_exp(x)
+#define R4_LOG(x) helpmath::r4_log(x)
+#define R4_LOG10(x) helpmath::r4_log10(x)
+#define R4_SIN(x) helpmath::r4_sin(x)
+#define R4_COS(x) helpmath::r4_cos(x)
+#define R4_TAN(x) helpmath::r4_tan(x)
+#define R4_ACOS(x) helpmath::r4_acos(x)
+#define R4_POW(x, y) helpmath::r4_pow(x, y)
+#define R4_SQRT(x) helpmath::r4_sqrt(x)
+#define R4_SQRTF(x) helpmath::r4_sqrt(x)
+#define R4_POW8(x) helpmath::r4_pow8(x)
+#define R4_POW7(x) helpmath::r4_pow7(x)
+#define R4_POW4(x) helpmath::r4_pow4(x)
+#define R8_POW(x, y) helpmath::det_pow(x, y)
+#define R8_LOG(x) helpmath::det_log(x)
+#define R8_ATAN(x) helpmath::det_atan(x)
+#define R8_SIN(x) helpmath::det_sin(x)
+#define R8_COS(x) helpmath::det_cos(x)
+#define R8_SQRT(x) helpmath::hm_sqrt(x)
+#endif
+
 namespace {
 
 typedef float r4;
@@ -171,7 +226,7 @@ struct Help {
   r4 PRCRI[22] = {0};
   // daily fluxes, DOUBLE PRECISION (F:93-95)
   r8 PRC[7] = {0}, DRN[7] = {0}, HED[7] = {0}, RCR[6] = {0}, RCRI[22] = {0};
-  int LD[6] = {0}, LP[7] = {0}, LPQ[7] = {0}, LCASE[6] = {0}, IYR = 0, IDA = 0, MO = 0,
+  int LD[8] = {0}, LP[8] = {0}, LPQ[8] = {0}, LCASE[8] = {0}, IYR = 0, IDA = 0, MO = 0,
       NSTEP[7] = {0}, ND = 0;
   int NSEGn[7] = {0}, NSEG = 0;          // NSEG1..NSEG6, NSEG
   r4 RM[13] = {0}, TM[13] = {0}, RLAT = 0;
@@ -334,11 +389,11 @@ struct Help {
       if (WP[J] <= 0.0f) WP[J] = 0.001f;
       if (FC[J] <= WP[J]) FC[J] = WP[J] + 0.001f;
       if (PORO[J] <= FC[J]) PORO[J] = FC[J] + 0.001f;
-      XLAMBD[J] = logf((FC[J] - RS[J]) / (WP[J] - RS[J])) / logf(45.f);
+      XLAMBD[J] = R4_LOG((FC[J] - RS[J]) / (WP[J] - RS[J])) / R4_LOG(45.f);
       r4 RELFC = (FC[J] - RS[J]) / (PORO[J] - RS[J]);
-      BUB[J] = (powf(RELFC, 1.f / XLAMBD[J])) * 1033.4f / 3.f;
+      BUB[J] = (R4_POW(RELFC, 1.f / XLAMBD[J])) * 1033.4f / 3.f;
       if (BUB[J] > 103.34f) BUB[J] = 103.34f;
-      CON[J] = (r4)(2.44f + (1485216.f * RC[J] * (powf(BUB[J] / 103.34f, (3.f * XLAMBD[J]) + 2.f))));
+      CON[J] = (r4)(2.44f + (1485216.f * RC[J] * (R4_POW(BUB[J] / 103.34f, (3.f * XLAMBD[J]) + 2.f))));
       if (RELFC < 0.20f) CON[J] = 3.30f;
       if (RC[J] < 0.000005f) CON[J] = 3.30f;
       if (CON[J] < 3.30f) CON[J] = 3.30f;
@@ -700,8 +755,8 @@ struct Help {
     r4 RCES = 0.0f;                                           // F:2296-2309
     for (int J = 1; J <= 7; ++J) RCES = RCES + WF[J] * RCUL[J];
     RCES = RCES / 34016.f;
-    RCES = -1.0f * log10f(RCES);
-    r4 SEDMX = 4.606745f * (powf(1.595155f, RCES));
+    RCES = -1.0f * R4_LOG10(RCES);
+    r4 SEDMX = 4.606745f * (R4_POW(1.595155f, RCES));
     if (SEDMX < 18.f) SEDMX = 18.f;
     if (SEDMX > 48.f) SEDMX = 48.f;
     if (EDEPTH > SEDMX) SEDEP = SEDMX; else SEDEP = EDEPTH;
@@ -710,7 +765,7 @@ struct Help {
   static r4 COMPUT(r4 AC, r4 A, r4 B, int I, int N) {         // F:2525-2531
     r4 AI = (r4)I - 0.5f, AN = (r4)N;
     r4 ANG = 6.283185f * AI / AN;
-    return AC + A * cosf(ANG) + B * sinf(ANG);
+    return AC + A * R4_COS(ANG) + B * R4_SIN(ANG);
   }
   static r4 AHU(int M, int K, r4 A1, r4 A2, r4 A3) {          // F:2484-2495
     r4 a = 0.f;
@@ -728,7 +783,7 @@ struct Help {
     for (int I = 1; I <= M; ++I) {
       r4 TI = (r4)I - 0.5f;
       r4 TH = 2.0f * PI * AN * TI;
-      r4 FCOS = cosf(TH / AM), FSIN = sinf(TH / AM);
+      r4 FCOS = R4_COS(TH / AM), FSIN = R4_SIN(TH / AM);
       SUMA = SUMA + D[I] * FCOS;
       SUMB = SUMB + D[I] * FSIN;
     }
@@ -780,13 +835,13 @@ struct Help {
       ST[I] = ST[I] / 25.4f;
     }
     ABD = ABD / (10.f * Z[7]);
-    r4 F = ABD / (ABD + 686.f * expf(-5.63f * ABD));
+    r4 F = ABD / (ABD + 686.f * R4_EXP(-5.63f * ABD));
     r4 DP = 1000.f + 2500.f * F;
     r4 WW = .356f - .144f * ABD;
-    r4 B = logf(500.f / DP);
+    r4 B = R4_LOG(500.f / DP);
     r4 WC = SWS / (WW * Z[7]);
     r4 q = (1.f - WC) / (1.f + WC);
-    F = expf(B * pw2(q));
+    F = R4_EXP(B * pw2(q));
     DD = F * DP;
   }
 
@@ -1007,13 +1062,13 @@ struct Help {
     for (int J = 1; J <= 7; ++J) CONA = CONA + (WF[J] * CONUL[J]);
     if (CONA < 3.3f) CONA = 3.3f;
     if (CONA > 5.1f) CONA = 5.1f;
-    STAGE1 = (23.f * powf(CONA - 3.0f, 0.42f)) / 25.4f;
+    STAGE1 = (23.f * R4_POW(CONA - 3.0f, 0.42f)) / 25.4f;
   }
 
   void POTET(r4& ETO1, r4& ETO2) {                            // F:3327-3436
     const r4 SALB = 0.23f;
     if (CV > 40000.f) CV = 40000.f;
-    EAJ = expf(-0.000029f * (CV + .1f));
+    EAJ = R4_EXP(-0.000029f * (CV + .1f));
     r4 ALB;
     if (SNO <= 5.f / 25.4f) {
       ALB = SALB;
@@ -1021,20 +1076,20 @@ struct Help {
     } else ALB = .6f;
     r4 TK = ((TMPF[IDA] - 32.0f) * 5.0f / 9.0f) + 273.0f;
     r4 TC = TK - 273.f;
-    r4 SVP = 33.8639f * (powf(0.00738f * TC + 0.8072f, 8.f) - 0.000019f * fabsf(1.8f * TC + 48.f) + 0.001316f);
+    r4 SVP = 33.8639f * (R4_POW8(0.00738f * TC + 0.8072f) - 0.000019f * fabsf(1.8f * TC + 48.f) + 0.001316f);
     r4 AVP = (RH[IDA] / 100.f) * SVP;
-    r4 DELTA = 33.8639f * (0.05904f * powf(0.00738f * TC + 0.8072f, 7.f) - 0.0000342f);
-    r4 RBO = 11.71E-8f * (0.39f - 0.05f * powf(AVP, 0.5f)) * powf(TK, 4.f);
+    r4 DELTA = 33.8639f * (0.05904f * R4_POW7(0.00738f * TC + 0.8072f) - 0.0000342f);
+    r4 RBO = 11.71E-8f * (0.39f - 0.05f * R4_SQRT(AVP)) * R4_POW4(TK);
     r4 XLAT = ULAT * 6.2832f / 360.f;
     r4 XI = (r4)IDA;
-    r4 SD = 0.4102f * sinf(0.0172f * (XI - 80.25f));
-    r4 CH = -tanf(XLAT) * tanf(SD);
+    r4 SD = 0.4102f * R4_SIN(0.0172f * (XI - 80.25f));
+    r4 CH = -R4_TAN(XLAT) * R4_TAN(SD);
     r4 H = 0.0f;
-    if (CH <= 1.0f && CH >= -1.0f) H = acosf(CH);
+    if (CH <= 1.0f && CH >= -1.0f) H = R4_ACOS(CH);
     else if (CH > 1.0f) H = 0.0f;
     else if (CH < -1.0f) H = 3.1416f;
-    r4 DDD = 1.0f + 0.0335f * sinf(0.0172f * (XI + 88.2f));
-    r4 RSO = 889.2305f * DDD * ((H * sinf(XLAT) * sinf(SD)) + (cosf(SD) * cosf(XLAT) * sinf(H)));
+    r4 DDD = 1.0f + 0.0335f * R4_SIN(0.0172f * (XI + 88.2f));
+    r4 RSO = 889.2305f * DDD * ((H * R4_SIN(XLAT) * R4_SIN(SD)) + (R4_COS(SD) * R4_COS(XLAT) * R4_SIN(H)));
     RSO = RSO * 0.8f;
     r4 ACOEF, BCOEF;
     if (RH[IDA] < 50) { ACOEF = 1.2f; BCOEF = -0.2f; }
@@ -1061,7 +1116,7 @@ struct Help {
     POTET(ETO1, ETO2);
     r4 TDEST = TA;
     if (PRE[IDA] == 0.0f)
-      TDEST = (powf(RH[IDA] / 100.f, 1.f / 8.f)) * (112.f + (0.9f * TA)) - 112.f + (0.1f * TA);
+      TDEST = (R4_POW(RH[IDA] / 100.f, 1.f / 8.f)) * (112.f + (0.9f * TA)) - 112.f + (0.1f * TA);
     if (SNO > 0.0f && TDEST >= TINDEX) {
       PINF = RAIN + SMELT + ADDRUN + GMRO - RUN;
       if (PINF < 0.0f) { RUN = RUN + PINF; if (RUN < 0.0f) RUN = 0.0f; }
@@ -1104,7 +1159,7 @@ struct Help {
       if (RAIN > 0.0f) {
         r4 ABSMAX = 0.05f;
         if (CV < 14000.f) ABSMAX = 0.05f * (CV + .1f) / 14000.f;
-        if ((RAIN / ABSMAX) < 88.f) ABST = ABSMAX * (1 - expf(-RAIN / ABSMAX));
+        if ((RAIN / ABSMAX) < 88.f) ABST = ABSMAX * (1 - R4_EXP(-RAIN / ABSMAX));
         else ABST = ABSMAX;
       }
       EABS = eta;
@@ -1150,7 +1205,7 @@ struct Help {
         ES = ES1;
       } else {
         TS2 = TS2 + 1.0f;
-        ES2 = CONA * (powf(TS2, 0.5f) - powf(TS2 - 1.0f, 0.5f)) / 25.4f;
+        ES2 = CONA * (R4_SQRT(TS2) - R4_SQRT(TS2 - 1.0f)) / 25.4f;
         if (ES2 >= ESO) { ES2 = ESO; eta = 0.0f; }
         else if (ES2 <= 0.0f) ES2 = 0.0f;
         else eta = eta - ES2;
@@ -1174,14 +1229,14 @@ struct Help {
     if (TMPC > TO) TGX = 2.f * TO - TB - TMPC;
     r4 RTO = pw2((TO - TMPC) / TGX);
     if (RTO > 200.f) TS = 0.f;
-    else TS = expf(-0.1054f * RTO);
+    else TS = R4_EXP(-0.1054f * RTO);
     if ((TMPC - 5.f) <= (AVT - 15.f)) TS = 0.f;
   }
 
   void CRPMOD() {                                             // F:3440-3512
     r4 WS = 0.f;
     r4 SUT = ST[7] * 25.4f / FCS[7];
-    r4 CDG = (.9f * TSEG[7] / (TSEG[7] + expf(9.93f - (.312f * TSEG[7])))) + .1f;
+    r4 CDG = (.9f * TSEG[7] / (TSEG[7] + R4_EXP(9.93f - (.312f * TSEG[7])))) + .1f;
     r4 DECR = .05f * fminf(CDG, SUT);
     RSD = RSD * (1.f - DECR);
     if (IPL == 0 && IDA == 30) GS = 0.f;
@@ -1216,7 +1271,7 @@ struct Help {
       r4 TGX = TMPC - TB;
       if (TGX > 0.f) TSTR(TGX, TMPC);
       else TS = 0.f;
-      r4 DDM = .5f * RAD[IDA] * (1.f - expf((-.65f) * (XLAI + .05f)));
+      r4 DDM = .5f * RAD[IDA] * (1.f - R4_EXP((-.65f) * (XLAI + .05f)));
       r4 REG = fminf(WS, TS);
       DM = DM + DDM * REG;
       if (DM <= 0.0f) DM = 0.0f;
@@ -1224,7 +1279,7 @@ struct Help {
       if (GS > .75f) XLAI = 16.f * DLAI * (1.f - GS) * (1.f - GS);
       else {
         r4 WLV = .8f * DM;
-        r4 F = WLV / (WLV + 5512 * expf((-0.000608f) * WLV));
+        r4 F = WLV / (WLV + 5512 * R4_EXP((-0.000608f) * WLV));
         XLAI = ULAI * F;
         DLAI = XLAI;
       }
@@ -1236,10 +1291,10 @@ struct Help {
   void SOLT() {                                               // F:3516-3560
     if (CV < 0.0f) CV = 0.0f;
     if (CV > 20000.f) CV = 20000.f;
-    r4 BCV = CV / (CV + expf(7.563f - (0.0001297f * CV)));
+    r4 BCV = CV / (CV + R4_EXP(7.563f - (0.0001297f * CV)));
     if ((SNO * 25.4f) > 120.f) BCV = fmaxf(1.f, BCV);
     else if (SNO > 0.0f) {
-      r4 XX = (SNO * 25.4f) / (SNO * 25.4f + expf(6.055f - (.3002f * SNO * 25.4f)));
+      r4 XX = (SNO * 25.4f) / (SNO * 25.4f + R4_EXP(6.055f - (.3002f * SNO * 25.4f)));
       BCV = fmaxf(XX, BCV);
     }
     r4 XI = (r4)IDA;
@@ -1249,10 +1304,10 @@ struct Help {
     if (RAD[IDA] == 0.f) ST0 = WFT[MO] * 5.f + TMPC;
     else ST0 = WFT[MO] * 5.f + TMPC - 5.f;
     r4 XX = BCV * TO + (1.f - BCV) * ST0;
-    r4 DT = XX - (AVT + AMP * cosf(ALX));
+    r4 DT = XX - (AVT + AMP * R4_COS(ALX));
     for (int K = 1; K <= 7; ++K) {
       r4 ZD = -Z[K] / DD;
-      if (fabsf(ZD) < 37.f) TSEG[K] = AVT + (AMP * cosf(ALX + ZD) + DT) * expf(ZD);
+      if (fabsf(ZD) < 37.f) TSEG[K] = AVT + (AMP * R4_COS(ALX + ZD) + DT) * R4_EXP(ZD);
       else TSEG[K] = AVT;
     }
   }
@@ -1355,7 +1410,7 @@ struct Help {
       if (IDN >= 275) X = (DAYN - 275.0f) / (458.0f - 275.0f);
       else if (IDN >= 92) X = (275.0f - DAYN) / (275.0f - 92.0f);
       else X = (91.0f + DAYN) / 183.0f;
-      r4 XX = (sinf(DAYN * 2.0f * 3.1416f / 366.0f) * 0.5f) + 0.5f;
+      r4 XX = (R4_SIN(DAYN * 2.0f * 3.1416f / 366.0f) * 0.5f) + 0.5f;
       r4 ADJMF;
       if (X <= 0.48f) ADJMF = 0.0f;
       else if (X >= 0.70f) ADJMF = 1.0f;
@@ -1363,7 +1418,7 @@ struct Help {
       r4 RMF60 = (XX * ADJMF * DIFF) + XMFMIN;
       r4 XMF = RMF60;
       if (fabsf(ULAT) < 60.0f) {
-        r4 RMF50 = (sinf(DAYN * 2.0f * 3.1416f / 366.0f) * DIFF * 0.5f) + (XMFMAX + XMFMIN) * 0.5f;
+        r4 RMF50 = (R4_SIN(DAYN * 2.0f * 3.1416f / 366.0f) * DIFF * 0.5f) + (XMFMAX + XMFMIN) * 0.5f;
         XMF = RMF50;
         if (fabsf(ULAT) > 50.0f) {
           r4 RINT = (fabsf(ULAT) - 50.f) / 10.f;
@@ -1383,7 +1438,7 @@ struct Help {
       if (TMX > 0.0f) XMELT = XMF * TMX;
       if (RAIN <= RFMIN) XMELT = XMELT + RAINM;
       else {
-        r4 SVP1 = powf(0.00738f * TA + 0.8072f, 8.f);
+        r4 SVP1 = R4_POW8(0.00738f * TA + 0.8072f);
         r4 SVP2 = 0.000019f * fabsf(1.8f * TA + 48.f);
         r4 SVP = 33.8639f * (SVP1 - SVP2 + 0.001316f);
         r4 AVP = 0.9f * SVP;
@@ -1424,14 +1479,14 @@ struct Help {
       FIT = 24;
       if (EXCESS != 0.0f) {
         if (EXCESS >= 0.1f && WE >= 1.0f) {
-          int N = (int)((powf(EXCESS * 4.0f, 0.3f)) + 0.5f);
+          int N = (int)((R4_POW(EXCESS * 4.0f, 0.3f)) + 0.5f);
           if (N == 0) N = 1;
           r4 FN = (r4)N;
           for (int I = 1; I <= N; ++I) {
             r4 FI = (r4)I;
             r4 TERM = 0.03f * WE * FN / (EXCESS * (FI - 0.5f));
             if (TERM > 50.0f) TERM = 50.0f;
-            r4 FLAG = 5.33f * (1.0f - expf(-TERM));
+            r4 FLAG = 5.33f * (1.0f - R4_EXP(-TERM));
             int L2 = (int)((FLAG + FIT) / FIT + 1.0f);
             int L1 = L2 - 1;
             r4 ENDL1 = (r4)(L1 * 24);
@@ -1448,9 +1503,9 @@ struct Help {
           r4 EL = EXLAG[1] / FIT;
           r4 ELS = EL / 25.4f;
           r4 WES = WE / 25.4f;
-          r4 TERM = 500.0f * ELS / (powf(WES, 1.3f));
+          r4 TERM = 500.0f * ELS / (R4_POW(WES, 1.3f));
           if (TERM > 50.0f) TERM = 50.0f;
-          r4 R1 = 1.0f / (5.0f * expf(-TERM) + 1.0f);
+          r4 R1 = 1.0f / (5.0f * R4_EXP(-TERM) + 1.0f);
           for (int I = 1; I <= 24; ++I) {
             r4 OS = (STORGE + EL) * R1;
             PACKRO = PACKRO + OS;
@@ -1516,22 +1571,22 @@ struct Help {
     if (DXLENG == 0.0) DXLENG = 1.0;
     if (!(TH > 0.0)) { DRNv = 0.0; return; }
     int ITER = 1;
-    r8 ALPHA = atan(DSLOPE);
+    r8 ALPHA = R8_ATAN(DSLOPE);
     r8 YSTAR = TH / DXLENG;
-    r8 QSTAR = 2.0f * YSTAR * sin(ALPHA) * cos(ALPHA);
+    r8 QSTAR = 2.0f * YSTAR * R8_SIN(ALPHA) * R8_COS(ALPHA);
     if (ALPHA <= 0.f) {
       QSTAR = dpw2((4.0 / PI) * YSTAR);
       DRNv = QSTAR * ELKS;
       return;
     }
-    r8 A = PI / 4.0 / cos(ALPHA);
-    r8 B = 2.0 * sqrt(0.4) / PI;
-    r8 C = 0.4 * dpw2(sin(ALPHA));
-    r8 D = 0.5 / log(B);
+    r8 A = PI / 4.0 / R8_COS(ALPHA);
+    r8 B = 2.0 * R8_SQRT(0.4) / PI;
+    r8 C = 0.4 * dpw2(R8_SIN(ALPHA));
+    r8 D = 0.5 / R8_LOG(B);
     if (YSTAR < (0.2f * DSLOPE)) { DRNv = QSTAR * ELKS; return; }
     r4 QSTARN;                       // implicit REAL*4 in the Fortran
     for (;;) {
-      r8 Fq = (A * (pow(B, pow(QSTAR / C, D))));
+      r8 Fq = (A * (R8_POW(B, R8_POW(QSTAR / C, D))));
       QSTARN = (r4)((YSTAR * YSTAR) / (Fq * Fq));
       r8 TOLER = 2.0f * fabs(QSTARN - QSTAR) / (QSTARN + QSTAR);
       if (EPS < TOLER && ITER < 10) {
@@ -1560,19 +1615,19 @@ struct Help {
       // Giroud radius-of-wetted-area form shared by the "contact" cases
       auto giroud = [&](r4 cp, r4 cd, r4 ex_h, r4 ex_k, r8 head) {
         if (PHOLE[LINER] > 0.0f) {
-          RPHOLE = cp * (pow(head, ex_h)) * (pow(RCS, ex_k));
-          HPHOLE = 1 + (head / (2.f * DTH * log(RPHOLE / 0.0005f)));
+          RPHOLE = cp * (R8_POW(head, ex_h)) * (R8_POW(RCS, ex_k));
+          HPHOLE = 1 + (head / (2.f * DTH * R8_LOG(RPHOLE / 0.0005f)));
           QPHOLE = (r4)(PHOLE[LINER] * 26.4f * RCS * HPHOLE * (dpw2(RPHOLE)));
         }
         if (DEFEC[LINER] > 0.0f) {
-          RDEFEC = cd * (pow(head, ex_h)) * (pow(RCS, ex_k));
-          HDEFEC = 1 + (head / (2.f * DTH * log(RDEFEC / 0.00564f)));
+          RDEFEC = cd * (R8_POW(head, ex_h)) * (R8_POW(RCS, ex_k));
+          HDEFEC = 1 + (head / (2.f * DTH * R8_LOG(RDEFEC / 0.00564f)));
           QDEFEC = (r4)(DEFEC[LINER] * 26.4f * RCS * HDEFEC * (dpw2(RDEFEC)));
         }
       };
       if (LC == 1) {
         QPHOLE = (r4)(PHOLE[LINER] * 0.000177f * TH / THICK[LINER]);
-        QDEFEC = (r4)(DEFEC[LINER] * 0.0356f * sqrt(TH));
+        QDEFEC = (r4)(DEFEC[LINER] * 0.0356f * R8_SQRT(TH));
       }
       if (LC == 2) {
         if (PQ == 1) {
@@ -1582,7 +1637,7 @@ struct Help {
         if (PQ > 1 && PQ < 5) giroud(0.00363f, 0.0229f, 0.38f, -0.25f, TH);
         if (PQ == 5) {
           QPHOLE = (r4)(PHOLE[LINER] * 0.000177f * TH / THICK[LINER]);
-          QDEFEC = (r4)(DEFEC[LINER] * 0.0356f * sqrt(TH));
+          QDEFEC = (r4)(DEFEC[LINER] * 0.0356f * R8_SQRT(TH));
         }
       }
       if (LC == 3) {
@@ -1595,7 +1650,7 @@ struct Help {
         if (PQ == 4) giroud(0.1053f, 0.134f, 0.45f, -0.13f, TH);
         if (PQ == 5) {
           QPHOLE = (r4)(PHOLE[LINER] * 0.000177f * TH / THICK[LINER]);
-          QDEFEC = (r4)(DEFEC[LINER] * 0.0356f * sqrt(TH));
+          QDEFEC = (r4)(DEFEC[LINER] * 0.0356f * R8_SQRT(TH));
         }
       }
       if (LC == 4) {
@@ -1608,7 +1663,7 @@ struct Help {
         if (PQ == 4) giroud(0.1053f, 0.134f, 0.45f, -0.13f, TH + DTH);
         if (PQ == 5) {
           QPHOLE = (r4)(PHOLE[LINER] * 0.000177f * (TH + DTH / THICK[LINER]));   // sic (F:5167-5168)
-          QDEFEC = (r4)(DEFEC[LINER] * 0.0356f * sqrt((TH + DTH)));
+          QDEFEC = (r4)(DEFEC[LINER] * 0.0356f * R8_SQRT((TH + DTH)));
         }
       }
       if (LC == 5 || LC == 6) {
@@ -1619,14 +1674,14 @@ struct Help {
           if (((RCS / 100.f) * 0.000001f) < (4.0f * TRANS[LINER] * head / 10000.f / 39.37f)) {
             for (int I = 1; I <= 10; ++I) {
               RSQR = (r4)(4.0f * TRANS[LINER] * head / 10000.f / 39.37f);
-              DENOM = (r4)(2.f * log(RPHOLE / 0.0005f));
+              DENOM = (r4)(2.f * R8_LOG(RPHOLE / 0.0005f));
               DENOM = (r4)(DENOM + (dpw2(0.0005f / RPHOLE)) - 1.0f);
               RSQR = (r4)((RSQR * 100.f) / RCS / DENOM);
-              RPHOLE = sqrtf(RSQR);
+              RPHOLE = R4_SQRTF(RSQR);
             }
           }
-          if (LC == 5) HPHOLE = 1 + (head / (2.f * DTH * log(RPHOLE / 0.0005f)));
-          else HPHOLE = 1 + (head / (2 * DTH * log(RPHOLE / 0.0005f)));
+          if (LC == 5) HPHOLE = 1 + (head / (2.f * DTH * R8_LOG(RPHOLE / 0.0005f)));
+          else HPHOLE = 1 + (head / (2 * DTH * R8_LOG(RPHOLE / 0.0005f)));
           QPHOLE = (r4)(PHOLE[LINER] * 26.4f * RCS * HPHOLE * dpw2(RPHOLE));
         }
         if (DEFEC[LINER] > 0.0f) {
@@ -1634,13 +1689,13 @@ struct Help {
             const r4 cdef = (LC == 5) ? 0.00564f : 0.00565f;   // sic (F:5214 vs F:5271)
             for (int I = 1; I <= 10; ++I) {
               RSQR = (r4)(4.0f * TRANS[LINER] * head / 10000.f / 39.37f);
-              DENOM = (r4)(2.f * log(RDEFEC / 0.00564f));
+              DENOM = (r4)(2.f * R8_LOG(RDEFEC / 0.00564f));
               DENOM = (r4)(DENOM + (dpw2(cdef / RDEFEC)) - 1.0f);
               RSQR = (r4)((RSQR * 100.f) / RCS / DENOM);
-              RDEFEC = sqrtf(RSQR);
+              RDEFEC = R4_SQRTF(RSQR);
             }
           }
-          HDEFEC = 1 + (head / (2.f * DTH * log(RDEFEC / 0.00564f)));
+          HDEFEC = 1 + (head / (2.f * DTH * R8_LOG(RDEFEC / 0.00564f)));
           QDEFEC = (r4)(DEFEC[LINER] * 26.4f * RCS * HDEFEC * dpw2(RDEFEC));
         }
       }
@@ -1693,9 +1748,9 @@ struct Help {
         RELMIN = (r4)((DWPUL[J + 1] - DRSUL[J + 1]) / (DUL[J + 1] - DRSUL[J + 1]));
         RELSW = (r4)((SWULY[J + 1] + (BALY[J + 1] / 2.0) - DRSUL[J + 1]) / (DUL[J + 1] - DRSUL[J + 1]));
         if (RELSW < RELMIN) RELSW = RELMIN;
-        PSIJP1 = (r4)(DBUBUL[J + 1] * (pow((r8)RELSW, -1.0f / DLAMUL[J + 1])));
+        PSIJP1 = (r4)(DBUBUL[J + 1] * (R8_POW((r8)RELSW, -1.0f / DLAMUL[J + 1])));
         if (PSIJP1 < DBUBUL[J]) PSIJP1 = (r4)DBUBUL[J];
-        RELSWL = (r4)pow(DBUBUL[J] / PSIJP1, DLAMUL[J]);
+        RELSWL = (r4)R8_POW(DBUBUL[J] / PSIJP1, DLAMUL[J]);
         SWLIM = (r4)((RELSWL * (DUL[J] - DRSUL[J])) + DRSUL[J]);
         if (SWLIM < DWPUL[J]) SWLIM = (r4)DWPUL[J];
         if (SWLIM > DFCUL[J]) SWLIM = (r4)DFCUL[J];
@@ -1745,17 +1800,17 @@ struct Help {
       }
       if (DRNMAX < 0.0) DRNMAX = 0.0;
       C = (3.0 + (2.0 / DLAMUL[J]));
-      LOW = DRCUL[J] * DT * pow((SWLIM - DRSUL[J]) / (DUL[J] - DRSUL[J]), C);
+      LOW = DRCUL[J] * DT * R8_POW((SWLIM - DRSUL[J]) / (DUL[J] - DRSUL[J]), C);
       if (LOW > DRNMAX) { DRIN[J + 1] = DRNMAX; goto L1070; }
       SWMAX = SWULY[J] + (0.5 * BALY[J]) + DSUB[J] + DRCR[J] + DRIN[J] - E[J];
       if (J == NSEGL && NSEGE == NSEG && IBAR > 3) SWMAX = SWMAX + DSUB[NSEGE];
       if (SWMAX > DUL[J]) SWMAX = DUL[J];
       if (SWMAX <= SWLIM) { DRIN[J + 1] = 0.0; goto L1070; }
-      HIGH = DRCUL[J] * DT * pow((SWMAX - DRSUL[J]) / (DUL[J] - DRSUL[J]), C);
+      HIGH = DRCUL[J] * DT * R8_POW((SWMAX - DRSUL[J]) / (DUL[J] - DRSUL[J]), C);
       if (HIGH > DRNMAX) HIGH = DRNMAX;
       SWMIN = SWMAX - HIGH;
       if (SWMIN < SWLIM) SWMIN = SWLIM;
-      LOW = DRCUL[J] * DT * pow((SWMIN - DRSUL[J]) / (DUL[J] - DRSUL[J]), C);
+      LOW = DRCUL[J] * DT * R8_POW((SWMIN - DRSUL[J]) / (DUL[J] - DRSUL[J]), C);
       if (LOW > DRNMAX) LOW = DRNMAX;
       SWMAX = SWULY[J] + (0.5 * BALY[J]) + DSUB[J] + DRCR[J] + DRIN[J] - E[J] - LOW;
       if (J == NSEGL && NSEGE == NSEG && IBAR > 3) SWMAX = SWMAX + DSUB[NSEGE];
@@ -1764,15 +1819,15 @@ struct Help {
       // Newton on f(x) = A - B x^C - 2x  (F:4461-4488)
       A = 2.0 * (SWULY[J] - DRSUL[J]) + BALY[J] + DRIN[J] + DSUB[J] + DRCR[J] - E[J];
       if (J == NSEGL && NSEGE == NSEG && IBAR > 3) A = A + (2.0 * DSUB[NSEGE]);
-      B = (DRCUL[J] * DT) * (pow(1.0 / (DUL[J] - DRSUL[J]), C));
+      B = (DRCUL[J] * DT) * (R8_POW(1.0 / (DUL[J] - DRSUL[J]), C));
       TOLER = 0.003 * (DUL[J] - DRSUL[J]);
       X0 = (SWMAX + SWMIN) / 2.0;
       {
         int ITER;
         for (ITER = 1; ITER <= 100; ++ITER) {
-          FX0 = A - (B * (pow(X0, C))) - (2 * X0);
+          FX0 = A - (B * (R8_POW(X0, C))) - (2 * X0);
           if (FX0 <= (0.3f * TOLER)) break;
-          FX0DER = -(B * C * (pow(X0, C - 1))) - 2;
+          FX0DER = -(B * C * (R8_POW(X0, C - 1))) - 2;
           if (fabs(FX0DER) < 1.0e-03) break;
           DX = FX0 / FX0DER;
           X0 = X0 - DX;
@@ -2133,6 +2188,15 @@ extern "C" int help_oracle_run(
           h.PRCA[n] = (r4)(h.PRCA[n] + h.PRC[n]);
         }
         h.RECIRC(IMO);
+#ifdef HELP_ORACLE_TRACE   // debugging aid: per-day state dump (build with -DHELP_ORACLE_TRACE)
+        {
+          fprintf(stderr, "D ipre %d day %d pinf %.9g ett %.9g es %.9g ep %.9g run %.9g addrun %.9g ifrez %d ET:", h.IPRE, h.IDA, h.PINF, h.ETT, h.ES, h.EP, h.RUN, h.ADDRUN, h.IFREZ);
+          for (int J = 1; J <= 7; ++J) fprintf(stderr, " %.9g", h.ET[J]);
+          fprintf(stderr, " SW:"); for (int J = 1; J <= h.NSEG; ++J) fprintf(stderr, " %.17g", h.DSWUL[J]);
+          fprintf(stderr, " BAL:"); for (int J = 1; J <= h.NSEG; ++J) fprintf(stderr, " %.17g", h.BALT[J]);
+          fprintf(stderr, "\n");
+        }
+#endif
         if (daily && h.IPRE >= 2) {                           // OUTDAY columns (F:5984-5996), inches
           double* d = daily + day_row * NDAILY;
           d[0] = h.PRE[IDA]; d[1] = h.RUN; d[2] = h.ETT; d[3] = SWE;
@@ -2235,3 +2299,46 @@ extern "C" int help_oracle_run(
 }
 
 extern "C" void help_oracle_clear_cache() { g_files.clear(); }
+
+// -----------------------------------------------------------------------------
+// Evaluate the transcendental functions this build uses (tests/test_help_math.py
+// checks the deterministic ones against mpmath and against the GPU's, bit for bit).
+// fn: 0 pow 1 exp 2 log 3 sin 4 cos 5 atan 6 acos(r4) 7 tan(r4) 8 r4_pow 9 r4_exp 10 r4_log
+//     11 r4_sin 12 r4_cos 13 r4_log10 14 r4_sqrt 15 r4_pow8 16 r4_pow7 17 r4_pow4
+// -----------------------------------------------------------------------------
+extern "C" int help_oracle_math_eval(int fn, const double* x, const double* y, double* out, long long n) {
+  for (long long i = 0; i < n; ++i) {
+    const double a = x[i], b = y ? y[i] : 0.0;
+    const float af = (float)a, bf = (float)b;
+    double r;
+    switch (fn) {
+      case 0: r = R8_POW(a, b); break;
+      case 1:
+#ifdef HELP_ORACLE_GLIBC
+        r = exp(a);
+#else
+        r = helpmath::det_exp(a);
+#endif
+        break;
+      case 2: r = R8_LOG(a); break;
+      case 3: r = R8_SIN(a); break;
+      case 4: r = R8_COS(a); break;
+      case 5: r = R8_ATAN(a); break;
+      case 6: r = R4_ACOS(af); break;
+      case 7: r = R4_TAN(af); break;
+      case 8: r = R4_POW(af, bf); break;
+      case 9: r = R4_EXP(af); break;
+      case 10: r = R4_LOG(af); break;
+      case 11: r = R4_SIN(af); break;
+      case 12: r = R4_COS(af); break;
+      case 13: r = R4_LOG10(af); break;
+      case 14: r = R4_SQRT(af); break;
+      case 15: r = R4_POW8(af); break;
+      case 16: r = R4_POW7(af); break;
+      case 17: r = R4_POW4(af); break;
+      default: return -1;
+    }
+    out[i] = r;
+  }
+  return 0;
+}

@@ -26,8 +26,13 @@ import subprocess
 import numpy as np
 
 _HERE = osp.dirname(osp.abspath(__file__))
-_LIB_PATH = osp.join(_HERE, "libhelp3o_oracle.so")
-_lib = None
+# Two builds of the same source (oracle/Makefile): "det" uses the deterministic
+# transcendentals of pyhelp_b200/csrc/help_math.h (the build the GPU engine must match
+# bit for bit), "glibc" the host libm a gfortran build of the reference would link.
+_LIB_PATHS = {"det": osp.join(_HERE, "libhelp3o_oracle.so"),
+              "glibc": osp.join(_HERE, "libhelp3o_oracle_glibc.so")}
+_LIB_PATH = _LIB_PATHS["det"]
+_libs = {}
 
 ROWS_MONTHLY = ("pre", "run", "et", "drn1", "drn2", "drn3", "drn4", "drn5",
                 "prc1", "prc2", "prc3", "prc4", "prc5", "prc6")
@@ -37,19 +42,20 @@ DAILY_COLS = ("pre", "run", "ett", "swe", "hed1", "drn1", "prc1", "hed2", "drn2"
 
 
 def build(force: bool = False) -> str:
-    """Compile the oracle shared library (gcc only; no CUDA, no reference code)."""
-    src = osp.join(_HERE, "help3o_oracle.cpp")
-    if force or not osp.exists(_LIB_PATH) or osp.getmtime(_LIB_PATH) < osp.getmtime(src):
-        subprocess.check_call(["make", "-C", _HERE, "-B", "libhelp3o_oracle.so"],
-                              stdout=subprocess.DEVNULL)
+    """Compile both oracle shared libraries (g++ only; no CUDA, no reference code)."""
+    deps = [osp.join(_HERE, "help3o_oracle.cpp"),
+            osp.join(_HERE, "..", "pyhelp_b200", "csrc", "help_math.h"),
+            osp.join(_HERE, "..", "pyhelp_b200", "csrc", "help_math_tables.h")]
+    newest = max(osp.getmtime(d) for d in deps)
+    if force or any(not osp.exists(p) or osp.getmtime(p) < newest for p in _LIB_PATHS.values()):
+        subprocess.check_call(["make", "-C", _HERE, "-B", "all"], stdout=subprocess.DEVNULL)
     return _LIB_PATH
 
 
-def _load():
-    global _lib
-    if _lib is None:
+def _load(libm: str = "det"):
+    if libm not in _libs:
         build()
-        lib = ctypes.CDLL(_LIB_PATH)
+        lib = ctypes.CDLL(_LIB_PATHS[libm])
         f = lib.help_oracle_run
         f.restype = ctypes.c_int
         c = ctypes
@@ -58,8 +64,29 @@ def _load():
                       c.c_int, c.c_float,
                       c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p,
                       c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p]
-        _lib = lib
-    return _lib
+        m = lib.help_oracle_math_eval
+        m.restype = ctypes.c_int
+        m.argtypes = [c.c_int, c.c_void_p, c.c_void_p, c.c_void_p, c.c_longlong]
+        _libs[libm] = lib
+    return _libs[libm]
+
+
+MATH_FN = {"pow": 0, "exp": 1, "log": 2, "sin": 3, "cos": 4, "atan": 5, "r4_acos": 6, "r4_tan": 7,
+           "r4_pow": 8, "r4_exp": 9, "r4_log": 10, "r4_sin": 11, "r4_cos": 12, "r4_log10": 13,
+           "r4_sqrt": 14, "r4_pow8": 15, "r4_pow7": 16, "r4_pow4": 17}
+
+
+def math_eval(fn: str, x, y=None, libm: str = "det") -> np.ndarray:
+    """Evaluate one of the oracle build's transcendental functions elementwise."""
+    lib = _load(libm)
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    yy = None if y is None else np.ascontiguousarray(y, dtype=np.float64)
+    out = np.empty_like(x)
+    rc = lib.help_oracle_math_eval(MATH_FN[fn], x.ctypes.data, None if yy is None else yy.ctypes.data,
+                                   out.ctypes.data, x.size)
+    if rc != 0:
+        raise ValueError(fn)
+    return out
 
 
 def _records(arr) -> tuple[bytes, int]:
@@ -73,11 +100,11 @@ def _records(arr) -> tuple[bytes, int]:
 
 def run_simulation(fpath_precip, fpath_tasavg, fpath_solrad, d11_input, d10_input,
                    fpath_output=None, iod=0, iom=1, ioa=0, ios=0, lmyr=1, tfsoil=32.0,
-                   *, daily: bool = False, full: bool = False):
+                   *, daily: bool = False, full: bool = False, libm: str = "det"):
     """One cell.  Returns the dict ``read_monthly_help_output`` would return
     (keys years/precip/runoff/evapo/subrun1/subrun2/perco/rechg); with
     ``full=True`` also the raw REAL*4 accumulators and diagnostics."""
-    lib = _load()
+    lib = _load(libm)
     d11b, n11 = _records(d11_input)
     d10b, n10 = _records(d10_input)
     ny = int(lmyr)
@@ -121,12 +148,18 @@ def _run_single(item):
     return name, run_simulation(*p)
 
 
-def run_help_allcells(cellparams: dict, ncore: int | None = None) -> dict:
+def _run_single_glibc(item):
+    name, p = item
+    return name, run_simulation(*p, libm="glibc")
+
+
+def run_help_allcells(cellparams: dict, ncore: int | None = None, libm: str = "det") -> dict:
     """Reference-shaped fan-out (pyhelp/processing.py:40-59) over the oracle."""
     ncore = max(mp.cpu_count() if ncore is None else ncore, 1)
-    _load()
+    _load(libm)
+    fn = _run_single if libm == "det" else _run_single_glibc
     if ncore == 1 or len(cellparams) < 2:
-        return dict(_run_single(it) for it in cellparams.items())
+        return dict(fn(it) for it in cellparams.items())
     with mp.get_context("fork").Pool(ncore) as pool:
         chunk = max(1, len(cellparams) // (ncore * 8))
-        return dict(pool.imap_unordered(_run_single, cellparams.items(), chunksize=chunk))
+        return dict(pool.imap_unordered(fn, cellparams.items(), chunksize=chunk))

@@ -1,0 +1,54 @@
+"""Build ``libhelp_b200.so`` in-tree with nvcc for sm_100a (no JIT cache, no torch)."""
+from __future__ import annotations
+
+import os
+import os.path as osp
+import shutil
+import subprocess
+import sys
+
+HERE = osp.dirname(osp.abspath(__file__))
+SRC = osp.join(HERE, "csrc")
+OUT = osp.join(HERE, "libhelp_b200.so")
+SOURCES = ["help_capi.cu"]
+DEPS = ["help_capi.cu", "help_sim.cuh", "help_setup.cuh", "help_image.h", "help_math.h", "help_math_tables.h",
+        "../../include/help_b200.h"]
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+    # every REAL*4 / REAL*8 operation rounds once, as in the reference's SSE2 code;
+    # contraction into FMA would move results away from the oracle (DESIGN.md "Numerics")
+    "-fmad=false",
+    "-Xcompiler", "-fPIC", "-shared",
+]
+
+
+def nvcc_path() -> str:
+    p = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not osp.exists(p):
+        raise RuntimeError("nvcc not found")
+    return p
+
+
+def needs_build() -> bool:
+    if not osp.exists(OUT):
+        return True
+    t = osp.getmtime(OUT)
+    return any(osp.getmtime(osp.join(SRC, d)) > t for d in DEPS)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if force or needs_build():
+        cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+            ["-o", OUT] + [osp.join(SRC, s) for s in SOURCES]
+        env = dict(os.environ)
+        r = subprocess.run(cmd, cwd=SRC, env=env, capture_output=True, text=True)
+        if verbose:
+            sys.stderr.write(r.stderr)
+        if r.returncode != 0:
+            raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

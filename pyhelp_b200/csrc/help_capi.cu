@@ -1,0 +1,390 @@
+// help_capi.cu -- the C ABI of include/help_b200.h over the sm_100a kernels.
+//
+// Launch plan of one simulate():
+//   1. help_setup_kernel (identity order)      -> class/cost sort key per cell
+//   2. cub::DeviceRadixSort (key, cell index)  -> perm: image slot -> cell
+//   3. help_setup_kernel (perm)                -> cell image in class order
+//   4. help_sim_kernel<MAXSEG>                 -> monthly / yearly / raw / flags
+// Weather is converted to the engine's internal units once at upload
+// (convert_weather_kernel).  No CPU fallback exists: every entry point fails
+// with HELP_B200_ENODEV when no CUDA device is usable.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cub/device/device_radix_sort.cuh>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/help_b200.h"
+#include "help_image.h"
+#include "help_setup.cuh"
+#include "help_sim.cuh"
+
+using namespace helpb200;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* what, cudaError_t ce = cudaSuccess) {
+  char buf[512];
+  if (ce != cudaSuccess) snprintf(buf, sizeof buf, "%s: %s", what, cudaGetErrorString(ce));
+  else snprintf(buf, sizeof buf, "%s", what);
+  g_err = buf;
+  return code;
+}
+
+#define CU(call)                                                            \
+  do {                                                                      \
+    cudaError_t _e = (call);                                                \
+    if (_e != cudaSuccess) return fail(_e == cudaErrorMemoryAllocation ? HELP_B200_ENOMEM : HELP_B200_ECUDA, #call, _e); \
+  } while (0)
+
+template <typename T>
+int dev_alloc(T** p, size_t count) {
+  *p = nullptr;
+  if (count == 0) count = 1;
+  CU(cudaMalloc((void**)p, count * sizeof(T)));
+  return 0;
+}
+
+__global__ void iota_kernel(int32_t* p, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = (int32_t)i;
+}
+
+}  // namespace
+
+struct help_b200_engine {
+  int device = 0;
+  BatchDev B{};
+  int64_t n = 0, stride = 0;
+  int ny = 0, segcap = 0, maxseg_t = 0;
+  bool want_monthly = false, want_raw = false, sort = true;
+  // device buffers owned by the engine
+  int32_t* d_years = nullptr;
+  float *d_pre = nullptr, *d_tmp = nullptr, *d_rad = nullptr, *d_tm = nullptr;
+  int32_t *d_iu4 = nullptr, *d_iu7 = nullptr, *d_iu13 = nullptr, *d_idfs = nullptr;
+  float *d_cell_f32 = nullptr, *d_layer_f32 = nullptr;
+  int32_t *d_cell_i32 = nullptr, *d_layer_i32 = nullptr;
+  double* d_layer_rc = nullptr;
+  float* d_img_f32 = nullptr; int32_t* d_img_i32 = nullptr; double* d_img_f64 = nullptr;
+  float *d_monthly = nullptr, *d_yearly = nullptr, *d_raw = nullptr;
+  uint32_t* d_flags = nullptr; int32_t* d_topo = nullptr;
+  uint64_t *d_key = nullptr, *d_key2 = nullptr; int32_t *d_perm = nullptr, *d_iota = nullptr;
+  void* d_cub = nullptr; size_t cub_bytes = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  float ms_h2d = 0, ms_setup = 0, ms_sim = 0;
+  int n_launches = 0;
+  double alg_bytes = 0;
+};
+
+static void engine_free(help_b200_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  void* ptrs[] = {e->d_years, e->d_pre, e->d_tmp, e->d_rad, e->d_tm, e->d_iu4, e->d_iu7, e->d_iu13, e->d_idfs,
+                  e->d_cell_f32, e->d_layer_f32, e->d_cell_i32, e->d_layer_i32, e->d_layer_rc, e->d_img_f32,
+                  e->d_img_i32, e->d_img_f64, e->d_monthly, e->d_yearly, e->d_raw, e->d_flags, e->d_topo,
+                  e->d_key, e->d_key2, e->d_perm, e->d_iota, e->d_cub};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  for (auto& ev : e->ev) if (ev) cudaEventDestroy(ev);
+  if (e->stream) cudaStreamDestroy(e->stream);
+  delete e;
+}
+
+static int validate(const help_b200_batch* b) {
+  if (!b) return fail(HELP_B200_EINVAL, "batch is NULL");
+  if (b->n_cells < 0 || b->n_years < 1 || b->n_years > HELP_B200_MAX_YEARS)
+    return fail(HELP_B200_EINVAL, "n_cells must be >= 0 and 1 <= n_years <= 100");
+  if (b->max_layers < 1 || b->max_layers > HELP_B200_MAX_LAYERS)
+    return fail(HELP_B200_EINVAL, "max_layers must be in 1..20");
+  if (b->n_nodes_p < 1 || b->n_nodes_t < 1 || b->n_nodes_r < 1)
+    return fail(HELP_B200_EINVAL, "at least one weather node per variable is required");
+  if (!b->years || !b->pre || !b->tmp || !b->rad || !b->iu4 || !b->iu7 || !b->iu13 || !b->tm_normals || !b->idfs)
+    return fail(HELP_B200_EINVAL, "a weather pointer is NULL");
+  if (b->n_cells > 0 && (!b->cell_f32 || !b->cell_i32 || !b->layer_f32 || !b->layer_i32 || !b->layer_rc))
+    return fail(HELP_B200_EINVAL, "a cell pointer is NULL");
+  return 0;
+}
+
+extern "C" double help_b200_algorithmic_bytes(const help_b200_batch* b) {
+  if (!b || b->n_cells <= 0) return 0.0;
+  const int64_t n = b->n_cells;
+  std::vector<uint8_t> sp(b->n_nodes_p, 0), st(b->n_nodes_t, 0), sr(b->n_nodes_r, 0);
+  double layers = 0;
+  for (int64_t c = 0; c < n; ++c) {
+    int p = b->cell_i32[HB_NODE_P * n + c], t = b->cell_i32[HB_NODE_T * n + c], r = b->cell_i32[HB_NODE_R * n + c];
+    if (p >= 0 && p < b->n_nodes_p) sp[p] = 1;
+    if (t >= 0 && t < b->n_nodes_t) st[t] = 1;
+    if (r >= 0 && r < b->n_nodes_r) sr[r] = 1;
+    layers += b->cell_i32[HB_NLAY * n + c];
+  }
+  double wp = 0, wt = 0, wr = 0;
+  for (auto v : sp) wp += v;
+  for (auto v : st) wt += v;
+  for (auto v : sr) wr += v;
+  double days = 0;
+  for (int y = 0; y < b->n_years; ++y) days += (b->years[y] % 4 == 0) ? 366 : 365;
+  // 12*W*D (3 variables x 4 B) + (56 + 36 L) per cell + 336 per cell-year (7 x 12 x 4 B)
+  return 4.0 * days * (wp + wt + wr) + 56.0 * n + 36.0 * layers + 336.0 * (double)n * b->n_years;
+}
+
+extern "C" int help_b200_abi_version(void) { return HELP_B200_ABI_VERSION; }
+extern "C" const char* help_b200_last_error(void) { return g_err.c_str(); }
+extern "C" int help_b200_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+extern "C" int help_b200_engine_create(const help_b200_batch* b, int want_monthly, int want_raw,
+                                       help_b200_engine** out) {
+  if (!out) return fail(HELP_B200_EINVAL, "out is NULL");
+  *out = nullptr;
+  int rc = validate(b);
+  if (rc) return rc;
+  if (help_b200_device_count() < 1) return fail(HELP_B200_ENODEV, "no CUDA device (this engine has no CPU path)");
+  help_b200_engine* e = new (std::nothrow) help_b200_engine();
+  if (!e) return fail(HELP_B200_ENOMEM, "host allocation failed");
+  auto bail = [&](int code) { engine_free(e); return code; };
+#define TRY(x) do { int _r = (x); if (_r) return bail(_r); } while (0)
+#define CUB_(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) return bail(fail(_e == cudaErrorMemoryAllocation ? HELP_B200_ENOMEM : HELP_B200_ECUDA, #call, _e)); } while (0)
+  CUB_(cudaGetDevice(&e->device));
+  CUB_(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  for (auto& ev : e->ev) CUB_(cudaEventCreate(&ev));
+  const int64_t n = b->n_cells;
+  const int ny = b->n_years, ml = b->max_layers;
+  e->n = n; e->ny = ny;
+  e->stride = ((n + 31) / 32) * 32;
+  if (e->stride == 0) e->stride = 32;
+  e->segcap = 7 + 3 * ml;
+  if (e->segcap > kMaxSeg) e->segcap = kMaxSeg;
+  e->maxseg_t = e->segcap <= 16 ? 16 : e->segcap <= 25 ? 25 : e->segcap <= 40 ? 40 : 67;
+  e->want_monthly = want_monthly != 0; e->want_raw = want_raw != 0;
+  const char* ns = getenv("HELP_B200_SORT");
+  e->sort = !(ns && ns[0] == '0');
+  e->alg_bytes = help_b200_algorithmic_bytes(b);
+  const size_t wrow = (size_t)ny * kDays;
+  TRY(dev_alloc(&e->d_years, ny));
+  TRY(dev_alloc(&e->d_pre, (size_t)b->n_nodes_p * wrow));
+  TRY(dev_alloc(&e->d_tmp, (size_t)b->n_nodes_t * wrow));
+  TRY(dev_alloc(&e->d_rad, (size_t)b->n_nodes_r * wrow));
+  TRY(dev_alloc(&e->d_tm, (size_t)b->n_nodes_t * 12));
+  TRY(dev_alloc(&e->d_iu4, b->n_nodes_p)); TRY(dev_alloc(&e->d_iu7, b->n_nodes_t)); TRY(dev_alloc(&e->d_iu13, b->n_nodes_r));
+  TRY(dev_alloc(&e->d_idfs, (size_t)b->n_nodes_r * 2));
+  TRY(dev_alloc(&e->d_cell_f32, (size_t)HB_NCELL_F32 * n)); TRY(dev_alloc(&e->d_cell_i32, (size_t)HB_NCELL_I32 * n));
+  TRY(dev_alloc(&e->d_layer_f32, (size_t)HL_NLAYER_F32 * ml * n));
+  TRY(dev_alloc(&e->d_layer_i32, (size_t)HL_NLAYER_I32 * ml * n));
+  TRY(dev_alloc(&e->d_layer_rc, (size_t)ml * n));
+  TRY(dev_alloc(&e->d_img_f32, (size_t)Image::n_f32(e->segcap) * e->stride));
+  TRY(dev_alloc(&e->d_img_i32, (size_t)Image::n_i32(e->segcap) * e->stride));
+  TRY(dev_alloc(&e->d_img_f64, (size_t)Image::n_f64() * e->stride));
+  if (e->want_monthly) TRY(dev_alloc(&e->d_monthly, (size_t)HR_NROWS * ny * 12 * n));
+  if (e->want_raw) TRY(dev_alloc(&e->d_raw, (size_t)HELP_B200_RAW_ROWS * ny * 12 * n));
+  TRY(dev_alloc(&e->d_yearly, (size_t)HY_NROWS * ny * n));
+  TRY(dev_alloc(&e->d_flags, n)); TRY(dev_alloc(&e->d_topo, (size_t)16 * n));
+  TRY(dev_alloc(&e->d_key, n)); TRY(dev_alloc(&e->d_key2, n)); TRY(dev_alloc(&e->d_perm, n)); TRY(dev_alloc(&e->d_iota, n));
+  CUB_(cub::DeviceRadixSort::SortPairs(nullptr, e->cub_bytes, e->d_key, e->d_key2, e->d_iota, e->d_perm, (int)n, 0, 64,
+                                       e->stream));
+  CUB_(cudaMalloc(&e->d_cub, e->cub_bytes ? e->cub_bytes : 1));
+  // ---- upload (timed) -----------------------------------------------------------------
+  cudaStream_t st = e->stream;
+  CUB_(cudaEventRecord(e->ev[0], st));
+#define H2D(dst, src, count) CUB_(cudaMemcpyAsync(dst, src, (size_t)(count) * sizeof(*(dst)), cudaMemcpyHostToDevice, st))
+  H2D(e->d_years, b->years, ny);
+  H2D(e->d_pre, b->pre, (size_t)b->n_nodes_p * wrow);
+  H2D(e->d_tmp, b->tmp, (size_t)b->n_nodes_t * wrow);
+  H2D(e->d_rad, b->rad, (size_t)b->n_nodes_r * wrow);
+  H2D(e->d_tm, b->tm_normals, (size_t)b->n_nodes_t * 12);
+  H2D(e->d_iu4, b->iu4, b->n_nodes_p); H2D(e->d_iu7, b->iu7, b->n_nodes_t); H2D(e->d_iu13, b->iu13, b->n_nodes_r);
+  H2D(e->d_idfs, b->idfs, (size_t)b->n_nodes_r * 2);
+  if (n > 0) {
+    H2D(e->d_cell_f32, b->cell_f32, (size_t)HB_NCELL_F32 * n); H2D(e->d_cell_i32, b->cell_i32, (size_t)HB_NCELL_I32 * n);
+    H2D(e->d_layer_f32, b->layer_f32, (size_t)HL_NLAYER_F32 * ml * n);
+    H2D(e->d_layer_i32, b->layer_i32, (size_t)HL_NLAYER_I32 * ml * n);
+    H2D(e->d_layer_rc, b->layer_rc, (size_t)ml * n);
+  }
+  {
+    const int th = 256;
+    auto blocks = [&](size_t total) { size_t g = (total + th - 1) / th; return (unsigned)(g > 148 * 16 ? 148 * 16 : (g ? g : 1)); };
+    size_t tp = (size_t)b->n_nodes_p * wrow, tt = (size_t)b->n_nodes_t * wrow, tr = (size_t)b->n_nodes_r * wrow;
+    convert_weather_kernel<<<blocks(tp), th, 0, st>>>(e->d_pre, e->d_iu4, (int64_t)wrow, (int64_t)tp, 0);
+    convert_weather_kernel<<<blocks(tt), th, 0, st>>>(e->d_tmp, e->d_iu7, (int64_t)wrow, (int64_t)tt, 1);
+    convert_weather_kernel<<<blocks(tr), th, 0, st>>>(e->d_rad, e->d_iu13, (int64_t)wrow, (int64_t)tr, 2);
+    if (n > 0) iota_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(e->d_iota, n);
+    e->n_launches += 3 + (n > 0 ? 1 : 0);
+  }
+  CUB_(cudaEventRecord(e->ev[1], st));
+  CUB_(cudaStreamSynchronize(st));
+  CUB_(cudaGetLastError());
+  CUB_(cudaEventElapsedTime(&e->ms_h2d, e->ev[0], e->ev[1]));
+  BatchDev& B = e->B;
+  B.n_cells = (int)n; B.n_years = ny; B.max_layers = ml;
+  B.n_nodes_p = b->n_nodes_p; B.n_nodes_t = b->n_nodes_t; B.n_nodes_r = b->n_nodes_r;
+  B.years = e->d_years; B.pre = e->d_pre; B.tmp = e->d_tmp; B.rad = e->d_rad;
+  B.iu4 = e->d_iu4; B.iu7 = e->d_iu7; B.iu13 = e->d_iu13; B.tm_normals = e->d_tm; B.idfs = e->d_idfs;
+  B.cell_f32 = e->d_cell_f32; B.cell_i32 = e->d_cell_i32; B.layer_f32 = e->d_layer_f32;
+  B.layer_i32 = e->d_layer_i32; B.layer_rc = e->d_layer_rc;
+  *out = e;
+  return 0;
+#undef H2D
+#undef TRY
+#undef CUB_
+}
+
+template <int MAXSEG>
+static void launch_sim(const SimArgs& A, int64_t n, cudaStream_t st) {
+  const int th = 64;
+  help_sim_kernel<MAXSEG><<<(unsigned)((n + th - 1) / th), th, 0, st>>>(A);
+}
+
+extern "C" int help_b200_engine_simulate(help_b200_engine* e, void* stream) {
+  if (!e) return fail(HELP_B200_EINVAL, "engine is NULL");
+  CU(cudaSetDevice(e->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
+  const int64_t n = e->n;
+  e->n_launches = 0;
+  Image img{e->d_img_f32, e->d_img_i32, e->d_img_f64, e->stride, e->segcap};
+  CU(cudaEventRecord(e->ev[0], st));
+  if (n > 0) {
+    const unsigned gs = (unsigned)((n + 63) / 64);
+    const int32_t* perm = nullptr;
+    if (e->sort) {
+      help_setup_kernel<<<gs, 64, 0, st>>>(e->B, img, nullptr, nullptr, nullptr, e->d_key);
+      CU(cub::DeviceRadixSort::SortPairs(e->d_cub, e->cub_bytes, e->d_key, e->d_key2, e->d_iota, e->d_perm, (int)n, 0, 64, st));
+      perm = e->d_perm;
+      e->n_launches += 2;   // + the radix-sort passes, which are library kernels and not counted
+    }
+    help_setup_kernel<<<gs, 64, 0, st>>>(e->B, img, perm, e->d_flags, e->d_topo, nullptr);
+    e->n_launches += 1;
+    CU(cudaEventRecord(e->ev[1], st));
+    SimArgs A;
+    A.img = img; A.pre = e->d_pre; A.tmp = e->d_tmp; A.rad = e->d_rad; A.years = e->d_years;
+    A.n_years = e->ny; A.n_cells = n; A.perm = perm;
+    A.monthly = e->d_monthly; A.yearly = e->d_yearly; A.raw = e->d_raw; A.flags = e->d_flags;
+    switch (e->maxseg_t) {
+      case 16: launch_sim<16>(A, n, st); break;
+      case 25: launch_sim<25>(A, n, st); break;
+      case 40: launch_sim<40>(A, n, st); break;
+      default: launch_sim<67>(A, n, st); break;
+    }
+    e->n_launches += 1;
+  } else {
+    CU(cudaEventRecord(e->ev[1], st));
+  }
+  CU(cudaEventRecord(e->ev[2], st));
+  CU(cudaStreamSynchronize(st));
+  CU(cudaGetLastError());
+  CU(cudaEventElapsedTime(&e->ms_setup, e->ev[0], e->ev[1]));
+  CU(cudaEventElapsedTime(&e->ms_sim, e->ev[1], e->ev[2]));
+  return 0;
+}
+
+extern "C" int help_b200_engine_device_ptrs(help_b200_engine* e, void** monthly, void** yearly, void** raw, void** flags) {
+  if (!e) return fail(HELP_B200_EINVAL, "engine is NULL");
+  if (monthly) *monthly = e->d_monthly;
+  if (yearly) *yearly = e->d_yearly;
+  if (raw) *raw = e->d_raw;
+  if (flags) *flags = e->d_flags;
+  return 0;
+}
+
+extern "C" int help_b200_engine_timings(help_b200_engine* e, float* ms_setup, float* ms_sim, int32_t* n_launches) {
+  if (!e) return fail(HELP_B200_EINVAL, "engine is NULL");
+  if (ms_setup) *ms_setup = e->ms_setup;
+  if (ms_sim) *ms_sim = e->ms_sim;
+  if (n_launches) *n_launches = e->n_launches;
+  return 0;
+}
+
+extern "C" int help_b200_engine_fetch(help_b200_engine* e, help_b200_result* r) {
+  if (!e || !r) return fail(HELP_B200_EINVAL, "engine or result is NULL");
+  CU(cudaSetDevice(e->device));
+  cudaStream_t st = e->stream;
+  const size_t n = (size_t)e->n, ny = (size_t)e->ny;
+  CU(cudaEventRecord(e->ev[0], st));
+  if (r->monthly) {
+    if (!e->d_monthly) return fail(HELP_B200_EINVAL, "monthly was not requested at engine_create");
+    CU(cudaMemcpyAsync(r->monthly, e->d_monthly, sizeof(float) * HR_NROWS * ny * 12 * n, cudaMemcpyDeviceToHost, st));
+  }
+  if (r->raw_monthly) {
+    if (!e->d_raw) return fail(HELP_B200_EINVAL, "raw_monthly was not requested at engine_create");
+    CU(cudaMemcpyAsync(r->raw_monthly, e->d_raw, sizeof(float) * HELP_B200_RAW_ROWS * ny * 12 * n, cudaMemcpyDeviceToHost, st));
+  }
+  if (r->yearly) CU(cudaMemcpyAsync(r->yearly, e->d_yearly, sizeof(float) * HY_NROWS * ny * n, cudaMemcpyDeviceToHost, st));
+  if (r->flags) CU(cudaMemcpyAsync(r->flags, e->d_flags, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, st));
+  if (r->topo) CU(cudaMemcpyAsync(r->topo, e->d_topo, sizeof(int32_t) * 16 * n, cudaMemcpyDeviceToHost, st));
+  CU(cudaEventRecord(e->ev[1], st));
+  CU(cudaStreamSynchronize(st));
+  CU(cudaEventElapsedTime(&r->ms_d2h, e->ev[0], e->ev[1]));
+  r->ms_h2d = e->ms_h2d; r->ms_setup = e->ms_setup; r->ms_simulate = e->ms_sim; r->n_launches = e->n_launches;
+  return 0;
+}
+
+extern "C" void help_b200_engine_destroy(help_b200_engine* e) { engine_free(e); }
+
+// ---- diagnostic: evaluate the engine's transcendental functions on the device -----------------
+__global__ void math_eval_kernel(int fn, const double* __restrict__ x, const double* __restrict__ y,
+                                 double* __restrict__ out, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double a = x[i], b = y ? y[i] : 0.0;
+  const float af = (float)a, bf = (float)b;
+  double r = 0.0;
+  switch (fn) {
+    case 0: r = r8_pow(a, b); break;
+    case 1: r = helpmath::det_exp(a); break;
+    case 2: r = r8_log(a); break;
+    case 3: r = r8_sin(a); break;
+    case 4: r = r8_cos(a); break;
+    case 5: r = r8_atan(a); break;
+    case 6: r = r4_acos(af); break;
+    case 7: r = r4_tan(af); break;
+    case 8: r = r4_pow(af, bf); break;
+    case 9: r = r4_exp(af); break;
+    case 10: r = r4_log(af); break;
+    case 11: r = r4_sin(af); break;
+    case 12: r = r4_cos(af); break;
+    case 13: r = r4_log10(af); break;
+    case 14: r = r4_sqrt(af); break;
+    case 15: r = r4_pow8(af); break;
+    case 16: r = r4_pow7(af); break;
+    case 17: r = r4_pow4(af); break;
+    default: break;
+  }
+  out[i] = r;
+}
+
+extern "C" int help_b200_math_eval(int fn, const double* x, const double* y, double* out, int64_t n) {
+  if (fn < 0 || fn > 17 || !x || !out || n < 0) return fail(HELP_B200_EINVAL, "math_eval: bad argument");
+  if (help_b200_device_count() < 1) return fail(HELP_B200_ENODEV, "no CUDA device (this engine has no CPU path)");
+  if (n == 0) return 0;
+  double *dx = nullptr, *dy = nullptr, *d_out = nullptr;
+  int rc = 0;
+  auto done = [&](int code) { if (dx) cudaFree(dx); if (dy) cudaFree(dy); if (d_out) cudaFree(d_out); return code; };
+  if ((rc = dev_alloc(&dx, (size_t)n)) || (rc = dev_alloc(&d_out, (size_t)n)) || (y && (rc = dev_alloc(&dy, (size_t)n)))) return done(rc);
+  cudaError_t ce = cudaMemcpy(dx, x, sizeof(double) * n, cudaMemcpyHostToDevice);
+  if (ce == cudaSuccess && y) ce = cudaMemcpy(dy, y, sizeof(double) * n, cudaMemcpyHostToDevice);
+  if (ce == cudaSuccess) {
+    math_eval_kernel<<<(unsigned)((n + 127) / 128), 128>>>(fn, dx, dy, d_out, n);
+    ce = cudaGetLastError();
+  }
+  if (ce == cudaSuccess) ce = cudaMemcpy(out, d_out, sizeof(double) * n, cudaMemcpyDeviceToHost);
+  if (ce != cudaSuccess) return done(fail(HELP_B200_ECUDA, "math_eval", ce));
+  return done(0);
+}
+
+extern "C" int help_b200_run(const help_b200_batch* b, help_b200_result* r) {
+  if (!r) return fail(HELP_B200_EINVAL, "result is NULL");
+  help_b200_engine* e = nullptr;
+  int rc = help_b200_engine_create(b, r->monthly != nullptr, r->raw_monthly != nullptr, &e);
+  if (rc) return rc;
+  rc = help_b200_engine_simulate(e, nullptr);
+  if (!rc) rc = help_b200_engine_fetch(e, r);
+  help_b200_engine_destroy(e);
+  return rc;
+}

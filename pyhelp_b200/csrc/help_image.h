@@ -1,0 +1,151 @@
+// help_image.h -- device-resident "cell image": everything the daily kernel needs
+// about one cell, produced once by the set-up kernel (help_setup.cuh) and read
+// by the simulation kernel (help_sim.cuh).
+//
+// Layout in HBM: structure of arrays, field-major, cell-minor
+//     f32[field][cell]   i32[field][cell]   f64[field][cell]
+// with `stride` (= n_cells rounded up to 32) between fields, so that the 32
+// threads of a warp (32 consecutive cells) read 128 contiguous bytes per
+// field.  Per-segment fields are laid out [field][segment][cell] with
+// `segcap` segments (the batch's upper bound, <= 67, HELP3O.FOR:70).
+//
+// Field meaning follows the reference's COMMON blocks (pyhelp/HELP3O.FOR:59-131);
+// the name of the Fortran variable is quoted next to each field.
+#pragma once
+#include <stdint.h>
+
+#ifndef HELP_R4_OVERRIDE
+#include "help_math.h"
+#endif
+
+namespace helpb200 {
+
+constexpr int kMaxLay = 20;
+constexpr int kMaxSeg = 67;
+constexpr int kNProf = 6;      // subprofiles (HELP3O.FOR:96-98)
+constexpr int kDays = 368;     // row stride of a weather year, floats (16 B aligned rows)
+
+// ---- f32 scalars ------------------------------------------------------------
+enum ImgF : int {
+  F_EDEPTH = 0,  // EDEPTH after unit conversion and liner clipping (F:1232,1498), in
+  F_SEDEP,       // SEDEP  max soil-evaporation depth (F:2296-2309)
+  F_SMXN,        // SCS retention parameter, unfrozen (F:169-174)
+  F_SMXF,        // ... frozen soil (F:178-185)
+  F_FRUNOF,      // FRUNOF/100 (F:1475)
+  F_CONA,        // CONA (F:3035-3040)
+  F_STAGE1,      // STAGE1 (F:3044)
+  F_ULAT, F_ULAI, F_WIND,            // after unit conversion (F:1233)
+  F_RH1, F_RH2, F_RH3, F_RH4,        // quarterly RH (F:1234-1245)
+  F_PHU, F_AVT, F_AMP, F_DD,         // INITIA (F:2411-2477)
+  F_Z7, F_FCS7, F_ST7,               // Z(7), FCS(7), initial ST(7) (F:2458-2465)
+  F_TS0, F_XLAI0, F_GS0, F_RSD0, F_DM0,  // vegetation start state (F:2413-2442)
+  F_OSNO,        // OSNO in inches (F:1476)
+  F_TFSOIL,      // TFSOIL, deg F
+  F_SUBINF,      // SUBINF (F:1465-1480)
+  F_NSCALAR
+};
+// ---- f32 per subprofile (6 each) ---------------------------------------------
+enum ImgPF : int {
+  P_DRCULS = 0,  // DRCUL(NSEGE) liner conductivity, in/day (F:4165)
+  P_DTHICS,      // DTHICK(NSEGE) liner (pseudo-)segment thickness (F:4164)
+  P_SLOPE,       // SLOPE(LAYD), percent, after SETUPS' zero fix (F:2602,4686)
+  P_XLENG,       // XLENG(LAYD), ft (F:2601,4687)
+  P_THKLIN,      // THICK(LINER) geomembrane thickness, in (F:4904)
+  P_PHOLE, P_DEFEC, P_TRANS,   // PHOLE/DEFEC/TRANS(LINER) (F:1482-1483)
+  P_RECIR,       // RECIR(LD(n)), percent of drainage recirculated (F:682)
+  P_SUBLIN,      // DSUB source term of the liner segment, DSUBIN(NSEGE) (F:4193)
+  P_NF
+};
+// ---- f32 per segment ----------------------------------------------------------
+enum ImgSF : int {
+  S_THICK = 0,   // STHICK   in
+  S_UL,          // UL       porosity * thickness, in
+  S_FC,          // FCUL
+  S_WP,          // WPUL
+  S_RS,          // RSUL     residual storage
+  S_LAM,         // XLAMBU   Brooks-Corey lambda
+  S_BUB,         // BUBUL    bubbling pressure
+  S_RC,          // RCUL     saturated K, in/day
+  S_SUBIN,       // SUBINS   subsurface inflow, in/day
+  S_SW0,         // SWUL     initial storage
+  S_NF
+};
+// ---- f64 per subprofile ---------------------------------------------------------
+enum ImgPD : int {
+  D_RCLIN = 0,   // RC(LINER), cm/s (F:4905)
+  D_RCS,         // RC(LAYSEG(NSEGE,1)) controlling-soil K, cm/s (F:4951)
+  D_NF
+};
+// ---- i32 scalars -------------------------------------------------------------------
+enum ImgI : int {
+  I_NSEG = 0, I_IPL, I_IHV, I_IDFS, I_NODE_P, I_NODE_T, I_NODE_R, I_FLAGS, I_NPROF, I_IPRE,
+  I_NSCALAR
+};
+// ---- i32 per subprofile --------------------------------------------------------------
+enum ImgPI : int {
+  Q_NSEGN = 0,   // NSEGn
+  Q_NSTEP,       // NSTEP(n) (F:2577-2672)
+  Q_IBAR,        // IBAR incl. the +3 subsurface-inflow cases (F:4166-4210)
+  Q_LAT,         // LAT (F:4179)
+  Q_LCASE,       // LCASE(n) (F:2074-2102)
+  Q_LPQ,         // LPQ(n)
+  Q_LTYPE,       // LAYER(LP(n)) (F:5292)
+  Q_LD,          // LD(n)
+  Q_NF
+};
+// i32 per segment: bit0 = LAYSEG(J,2) < LD(NPROF) (F:4494,4499)
+
+struct Image {
+  float* f32;
+  int32_t* i32;
+  double* f64;
+  int64_t stride;   // cells per field row
+  int segcap;
+
+  __host__ __device__ static int64_t n_f32(int segcap) { return F_NSCALAR + P_NF * kNProf + (int64_t)S_NF * segcap; }
+  __host__ __device__ static int64_t n_i32(int segcap) { return I_NSCALAR + Q_NF * kNProf + segcap; }
+  __host__ __device__ static int64_t n_f64() { return D_NF * kNProf; }
+
+  __device__ __forceinline__ float& F(int f, int64_t c) const { return f32[(int64_t)f * stride + c]; }
+  __device__ __forceinline__ float& PF(int f, int n, int64_t c) const {   // n = 1..6
+    return f32[(int64_t)(F_NSCALAR + f * kNProf + (n - 1)) * stride + c];
+  }
+  __device__ __forceinline__ float& SF(int f, int j, int64_t c) const {   // j = 1..segcap
+    return f32[(int64_t)(F_NSCALAR + P_NF * kNProf + f * segcap + (j - 1)) * stride + c];
+  }
+  __device__ __forceinline__ int32_t& I(int f, int64_t c) const { return i32[(int64_t)f * stride + c]; }
+  __device__ __forceinline__ int32_t& PI(int f, int n, int64_t c) const {
+    return i32[(int64_t)(I_NSCALAR + f * kNProf + (n - 1)) * stride + c];
+  }
+  __device__ __forceinline__ int32_t& SI(int j, int64_t c) const {
+    return i32[(int64_t)(I_NSCALAR + Q_NF * kNProf + (j - 1)) * stride + c];
+  }
+  __device__ __forceinline__ double& PD(int f, int n, int64_t c) const {
+    return f64[(int64_t)(f * kNProf + (n - 1)) * stride + c];
+  }
+};
+
+// cell status bits (mirrors include/help_b200.h)
+constexpr uint32_t kFlagNonConv = 0x1u, kFlagNaN = 0x2u, kFlagOverflow = 0x4u, kFlagRecirc = 0x8u,
+                   kFlagBadCell = 0x10u;
+
+// ---- transcendental functions ------------------------------------------------------------
+// The reference's surface-process code is REAL*4 and its routing code REAL*8; both get
+// their transcendentals from libm.  HELP is chaotic in the last bit of those functions
+// (help_math.h), so the engine uses the deterministic implementations of help_math.h --
+// the same ones the CPU oracle is built with -- instead of CUDA's libdevice:
+//   r4_*(x): REAL*4 intrinsic = correctly rounded float (evaluated in double, rounded once)
+//   r8_*(x): REAL*8 intrinsic, < 1 ulp
+#ifndef HELP_R4_OVERRIDE   // (scripts/host_emu swaps in glibc's libm to separate logic from libm differences)
+using helpmath::r4_exp; using helpmath::r4_log; using helpmath::r4_log10; using helpmath::r4_sin;
+using helpmath::r4_cos; using helpmath::r4_tan; using helpmath::r4_acos; using helpmath::r4_pow;
+using helpmath::r4_sqrt; using helpmath::r4_pow8; using helpmath::r4_pow7; using helpmath::r4_pow4;
+__host__ __device__ __forceinline__ double r8_pow(double x, double y) { return helpmath::det_pow(x, y); }
+__host__ __device__ __forceinline__ double r8_log(double x) { return helpmath::det_log(x); }
+__host__ __device__ __forceinline__ double r8_atan(double x) { return helpmath::det_atan(x); }
+__host__ __device__ __forceinline__ double r8_sin(double x) { return helpmath::det_sin(x); }
+__host__ __device__ __forceinline__ double r8_cos(double x) { return helpmath::det_cos(x); }
+__host__ __device__ __forceinline__ double r8_sqrt(double x) { return helpmath::hm_sqrt(x); }
+#endif
+
+}  // namespace helpb200

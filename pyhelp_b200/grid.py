@@ -1,0 +1,188 @@
+"""Grid-level fast path: PyHELP's input grid + weather tables -> engine batch,
+without going through one text record per cell.
+
+This is the vectorised equivalent of what ``HelpManager.calc_help_cells`` does
+per cell before the hot path (reference ``pyhelp/managers.py:234-340,393-428``):
+
+* nearest weather node per cell (``_generate_d4d7d13_input_files``,
+  managers.py:300-334, haversine ``pyhelp/utils.py:81-96``),
+* D10/D11 formatting (``pyhelp/preprocessing.py:27-185``) and D4/D7/D13
+  formatting (``pyhelp/weather_reader.py:22-104``).
+
+The reference's formatters QUANTISE the inputs: precipitation to
+0.1 mm, temperature to 0.1 C, radiation to 0.01 MJ/m2, CN and thickness to
+integers, porosities to 3 decimals ...  ``quantize`` reproduces Python's
+``format(x, '.Nf')`` (round-half-even on the exact binary value) and the
+Fortran read that follows, so a batch built here is bit-identical to the batch
+parsed back from the reference's text (tests/test_inputs.py proves it).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _native as N
+from .inputs import CellBatch, F32, idfs_prescan
+
+MINEDEPTH, MAXEDEPTH, MINTHICK = 3, 80, 10        # preprocessing.py:20-22
+
+
+def quantize(x, d: int) -> np.ndarray:
+    """float(format(x, f'.{d}f')) element-wise, vectorised."""
+    x = np.asarray(x, dtype=np.float64)
+    s = 10.0 ** d
+    p = x * s
+    r = np.rint(p)
+    frac = np.abs(p - np.trunc(p))
+    near_tie = np.abs(frac - 0.5) < 1e-6
+    out = r / s
+    if near_tie.any():
+        flat, idx = out.reshape(-1), np.nonzero(near_tie.reshape(-1))[0]
+        xs = x.reshape(-1)
+        for i in idx:
+            flat[i] = float(format(xs[i], f".{d}f"))
+        out = flat.reshape(x.shape)
+    return out + 0.0          # -0.0 -> 0.0 is irrelevant to the Fortran read
+
+
+def calc_dist_from_coord(lat1, lon1, lat2, lon2):
+    """Haversine distance in km (reference pyhelp/utils.py:81-96)."""
+    lat1, lon1 = np.radians(lat1), np.radians(lon1)
+    lat2, lon2 = np.radians(lat2), np.radians(lon2)
+    r = 6373
+    dlon = lon2 - lon1
+    dlat = lat2 - lat1
+    a = np.sin(dlat / 2) ** 2 + np.cos(lat1) * np.cos(lat2) * np.sin(dlon / 2) ** 2
+    c = 2 * np.arctan2(np.sqrt(a), np.sqrt(1 - a))
+    return r * c
+
+
+def nearest_nodes(cell_lat, cell_lon, node_lat, node_lon, chunk: int = 8192) -> np.ndarray:
+    """argmin of the haversine distance per cell (first minimum wins, like np.argmin
+    in managers.py:313), evaluated in cell chunks to bound memory."""
+    cell_lat, cell_lon = np.asarray(cell_lat, float), np.asarray(cell_lon, float)
+    node_lat, node_lon = np.asarray(node_lat, float), np.asarray(node_lon, float)
+    out = np.empty(cell_lat.shape[0], dtype=np.int32)
+    for a in range(0, cell_lat.shape[0], chunk):
+        b = min(a + chunk, cell_lat.shape[0])
+        d = calc_dist_from_coord(cell_lat[a:b, None], cell_lon[a:b, None], node_lat[None, :], node_lon[None, :])
+        out[a:b] = np.argmin(d, axis=1)
+    return out
+
+
+def weather_to_nodes(years_of_day: np.ndarray, values: np.ndarray, decimals: int):
+    """[day][node] table -> [node][year][368] float32 as the engine reads a D4/D7/D13
+    file written by weather_reader.py (values quantised to `decimals`)."""
+    years_of_day = np.asarray(years_of_day)
+    years = np.unique(years_of_day)
+    nn = values.shape[1]
+    out = np.zeros((nn, years.size, N.DAYS), dtype=F32)
+    q = quantize(values, decimals).astype(F32)
+    for k, y in enumerate(years):
+        sel = np.nonzero(years_of_day == y)[0]
+        nd = 366 if (y % 4 == 0 and (y % 100 != 0 or y % 400 == 0)) else 365      # calendar.isleap (weather_reader.py:87)
+        if sel.size != nd:
+            raise ValueError(f"year {y} has {sel.size} days of data, expected {nd}")
+        out[:, k, :nd] = q[sel].T
+    return years.astype(np.int32), out
+
+
+def batch_from_grid(grid: dict, years_of_day, precip, airtemp, solrad, node_p, node_t, node_r,
+                    solrad_lat=None, tfsoil_c: float = 0.0, sf_edepth: float = 1.0, sf_ulai: float = 1.0,
+                    sf_cn: float = 1.0, extra_layers: dict | None = None) -> CellBatch:
+    """Vectorised `format_d10d11_inputs` + weather formatting + Fortran read.
+
+    ``grid``: mapping column -> array over cells with the columns of docs/data.rst
+    (cid, lat_dd, wind, hum1-4, growth_start, growth_end, LAI, EZD, CN, nlayer,
+    lay_type{i}, thick{i}, poro{i}, fc{i}, wp{i}, ksat{i}, dist_dr{i}, slope{i}).
+    ``precip``/``airtemp``/``solrad``: [day][node] tables in mm, deg C, MJ/m2/day.
+    ``extra_layers``: optional per-layer design fields PyHELP's formatter leaves blank
+    (phole{i}, defec{i}, ipq{i}, trans{i}, recir{i}, subin{i}) for landfill designs.
+    Cells PyHELP would skip (nlayer == 0 or a -9999 layer field,
+    preprocessing.py:32-35,150-153) must be removed by the caller (`runnable_cells`).
+    """
+    g = {k: np.asarray(v) for k, v in grid.items()}
+    n = int(np.asarray(g["nlayer"]).shape[0])
+    nlay = g["nlayer"].astype(np.int32)
+    L = int(nlay.max()) if n else 1
+    cell_f32 = np.zeros((N.HB_NCELL_F32, n), dtype=F32)
+    cell_i32 = np.zeros((N.HB_NCELL_I32, n), dtype=np.int32)
+    # D11 (preprocessing.py:63-74)
+    cell_f32[N.HB_ULAT] = quantize(g["lat_dd"], 2)
+    cell_f32[N.HB_ULAI] = quantize(g["LAI"].astype(float) * sf_ulai, 2)
+    ezd = np.minimum(np.maximum(g["EZD"].astype(float) * sf_edepth, MINEDEPTH), MAXEDEPTH)
+    cell_f32[N.HB_EDEPTH] = quantize(ezd, 1)
+    cell_f32[N.HB_WIND] = quantize(g["wind"], 1)
+    for q in range(4):
+        cell_f32[N.HB_HUM1 + q] = quantize(g[f"hum{q + 1}"], 1)
+    cell_i32[N.HB_IU11] = 2
+    cell_i32[N.HB_IPL] = g["growth_start"].astype(np.int32)
+    cell_i32[N.HB_IHV] = g["growth_end"].astype(np.int32)
+    # D10 header (preprocessing.py:93-128): iu10=2, ipre=0, osno=0, frunof=100, irun=1
+    cell_i32[N.HB_IU10] = 2
+    cell_i32[N.HB_IPRE] = 0
+    cell_f32[N.HB_OSNO] = 0.0
+    cell_f32[N.HB_FRUNOF] = 100.0
+    cell_f32[N.HB_CN2] = quantize(g["CN"].astype(float) * sf_cn, 0)
+    cell_f32[N.HB_TFSOIL] = F32((tfsoil_c * 1.8) + 32)          # managers.py:387
+    cell_i32[N.HB_NLAY] = nlay
+    cell_i32[N.HB_NODE_P] = np.asarray(node_p, dtype=np.int32)
+    cell_i32[N.HB_NODE_T] = np.asarray(node_t, dtype=np.int32)
+    cell_i32[N.HB_NODE_R] = np.asarray(node_r, dtype=np.int32)
+    layer_f32 = np.zeros((N.HL_NLAYER_F32, L, n), dtype=F32)
+    layer_i32 = np.zeros((N.HL_NLAYER_I32, L, n), dtype=np.int32)
+    layer_rc = np.zeros((L, n), dtype=np.float64)
+    ex = extra_layers or {}
+    for j in range(L):
+        s = str(j + 1)
+        on = nlay > j
+        if f"lay_type{s}" not in g:
+            continue
+        def col(name, default=0.0):
+            a = g.get(name + s, ex.get(name + s))
+            return np.where(on, np.asarray(a, dtype=float), 0.0) if a is not None else np.full(n, default) * on
+        layer_i32[N.HL_TYPE, j] = np.where(on, g[f"lay_type{s}"].astype(np.int32), 0)
+        layer_f32[N.HL_THICK, j] = np.where(on, quantize(np.maximum(col("thick"), MINTHICK), 0), 0)
+        layer_f32[N.HL_PORO, j] = quantize(col("poro"), 3)
+        layer_f32[N.HL_FC, j] = quantize(col("fc"), 3)
+        layer_f32[N.HL_WP, j] = quantize(col("wp"), 3)
+        layer_rc[j] = quantize(col("ksat"), 14)
+        layer_f32[N.HL_XLENG, j] = quantize(col("dist_dr"), 0)
+        layer_f32[N.HL_SLOPE, j] = quantize(col("slope"), 2)
+        if ex:
+            layer_f32[N.HL_PHOLE, j] = col("phole")
+            layer_f32[N.HL_DEFEC, j] = col("defec")
+            layer_f32[N.HL_TRANS, j] = col("trans")
+            layer_f32[N.HL_RECIR, j] = col("recir")
+            layer_f32[N.HL_SUBIN, j] = col("subin")
+            layer_i32[N.HL_IPQ, j] = col("ipq").astype(np.int32)
+            if f"thick_exact{s}" in ex:          # landfill liners are thinner than MINTHICK
+                layer_f32[N.HL_THICK, j] = np.where(on, np.asarray(ex[f"thick_exact{s}"], dtype=float), 0)
+    years, pre = weather_to_nodes(years_of_day, np.asarray(precip, float), 1)
+    _, tmp = weather_to_nodes(years_of_day, np.asarray(airtemp, float), 1)
+    _, rad = weather_to_nodes(years_of_day, np.asarray(solrad, float), 2)
+    npn, ntn, nrn = pre.shape[0], tmp.shape[0], rad.shape[0]
+    idfs = np.array([idfs_prescan(rad[i, :, :366], 2) for i in range(nrn)], dtype=np.int32).reshape(-1, 2)
+    names = [str(c) for c in g["cid"].tolist()] if "cid" in g else [str(i) for i in range(n)]
+    return CellBatch(
+        n, int(years.size), L, np.ascontiguousarray(years), pre, tmp, rad,
+        np.full(npn, 2, dtype=np.int32), np.full(ntn, 2, dtype=np.int32), np.full(nrn, 2, dtype=np.int32),
+        np.zeros((ntn, 12), dtype=F32), np.ascontiguousarray(idfs),
+        cell_f32, cell_i32, np.ascontiguousarray(layer_f32), np.ascontiguousarray(layer_i32),
+        np.ascontiguousarray(layer_rc), names)
+
+
+def runnable_cells(grid: dict) -> np.ndarray:
+    """Mask of cells PyHELP would run (preprocessing.py:32-35,150-153; managers.py `run`)."""
+    g = {k: np.asarray(v) for k, v in grid.items()}
+    nlay = g["nlayer"].astype(int)
+    ok = nlay > 0
+    if "run" in g:
+        ok &= g["run"].astype(int) == 1
+    for j in range(int(nlay.max()) if nlay.size else 0):
+        s = str(j + 1)
+        on = nlay > j
+        # (thick is max()-ed with MINTHICK before the reference's -9999 test, so it never trips it)
+        for name in ("poro", "fc", "wp", "ksat", "dist_dr", "slope"):
+            if name + s in g:
+                ok &= ~(on & (g[name + s].astype(float) == -9999))
+    return ok

@@ -1,0 +1,171 @@
+"""Drop-in for the reference's ``pyhelp/processing.py`` hot path, on the B200 engine.
+
+Reference functions mirrored here (same names, arguments, return values):
+
+* :func:`run_help_allcells` -- ``pyhelp/processing.py:40-59``.  Takes the
+  ``cellparams`` dict ``HelpManager.calc_help_cells`` builds
+  (``pyhelp/managers.py:393-428``) and returns ``{cellname: {'years', 'precip',
+  'runoff', 'evapo', 'subrun1', 'subrun2', 'perco', 'rechg'}}`` with the dtypes
+  and shapes of ``read_monthly_help_output`` (``pyhelp/processing.py:139-146``).
+  The reference runs one Fortran call + one text file per cell in a
+  ``multiprocessing.Pool``; here the whole dict becomes one GPU batch.
+  Differences, both deliberate: results come back in ``cellparams`` order (the
+  reference's ``imap_unordered`` order is nondeterministic) and
+  ``ncore`` is accepted and ignored.
+* :func:`run_help_singlecell` -- ``pyhelp/processing.py:30-37``.
+
+:class:`HelpEngine` is the batch-level API underneath (upload once, simulate,
+fetch), used by ``bench.py`` and by callers that want the arrays rather than
+per-cell dicts.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import time
+
+import numpy as np
+
+from . import _native as N
+from .inputs import CellBatch, batch_from_cellparams
+
+KEYS = ("precip", "runoff", "evapo", "subrun1", "subrun2", "perco", "rechg")
+
+
+class HelpEngine:
+    """Resident GPU engine for one :class:`CellBatch` (``help_b200_engine_*``)."""
+
+    def __init__(self, batch: CellBatch, monthly: bool = True, raw: bool = False):
+        N.require_device()
+        self.batch = batch
+        self._struct = batch.as_struct()
+        self._h = C.c_void_p()
+        self.want_monthly, self.want_raw = monthly, raw
+        N.check(N.lib().help_b200_engine_create(C.byref(self._struct), int(monthly), int(raw),
+                                                C.byref(self._h)), "engine_create")
+
+    def simulate(self, stream: int | None = None):
+        N.check(N.lib().help_b200_engine_simulate(self._h, C.c_void_p(stream) if stream else None),
+                "engine_simulate")
+        ms_setup, ms_sim, nl = C.c_float(), C.c_float(), C.c_int32()
+        N.lib().help_b200_engine_timings(self._h, C.byref(ms_setup), C.byref(ms_sim), C.byref(nl))
+        self.ms_setup, self.ms_simulate, self.n_launches = ms_setup.value, ms_sim.value, nl.value
+        return self
+
+    def device_ptrs(self) -> dict:
+        p = [C.c_void_p() for _ in range(4)]
+        N.check(N.lib().help_b200_engine_device_ptrs(self._h, *[C.byref(x) for x in p]), "device_ptrs")
+        return dict(zip(("monthly", "yearly", "raw", "flags"), [x.value for x in p]))
+
+    def fetch(self, monthly: bool | None = None, yearly: bool = True, raw: bool | None = None,
+              topo: bool = False) -> dict:
+        b = self.batch
+        n, ny = b.n_cells, b.n_years
+        monthly = self.want_monthly if monthly is None else monthly
+        raw = self.want_raw if raw is None else raw
+        out = {"flags": np.zeros(n, dtype=np.uint32)}
+        if monthly:
+            out["monthly"] = np.empty((N.HR_NROWS, ny, 12, n), dtype=np.float32)
+        if yearly:
+            out["yearly"] = np.empty((N.HY_NROWS, ny, n), dtype=np.float32)
+        if raw:
+            out["raw"] = np.empty((N.RAW_ROWS, ny, 12, n), dtype=np.float32)
+        if topo:
+            out["topo"] = np.zeros((16, n), dtype=np.int32)
+        r = N.Result()
+        r.monthly, r.yearly, r.raw_monthly = N.ptr(out.get("monthly")), N.ptr(out.get("yearly")), N.ptr(out.get("raw"))
+        r.flags, r.topo = N.ptr(out["flags"]), N.ptr(out.get("topo"))
+        N.check(N.lib().help_b200_engine_fetch(self._h, C.byref(r)), "engine_fetch")
+        out["timing_ms"] = {"h2d": r.ms_h2d, "setup": r.ms_setup, "simulate": r.ms_simulate, "d2h": r.ms_d2h}
+        out["n_launches"] = r.n_launches
+        out["years"] = b.years.astype(np.uint16)
+        return out
+
+    def close(self):
+        if self._h:
+            N.lib().help_b200_engine_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def run_batch(batch: CellBatch, monthly: bool = True, raw: bool = False, topo: bool = False) -> dict:
+    """One-shot: upload, simulate, fetch (host buffers in and out)."""
+    with HelpEngine(batch, monthly=monthly, raw=raw) as eng:
+        eng.simulate()
+        return eng.fetch(topo=topo)
+
+
+def split_by_cell(batch: CellBatch, res: dict) -> dict:
+    """[row][year][month][cell] -> the reference's dict of per-cell dicts."""
+    years = res["years"]
+    per_cell = np.ascontiguousarray(np.transpose(res["monthly"], (3, 0, 1, 2)))   # (n, 7, ny, 12)
+    out = {}
+    for i, name in enumerate(batch.names):
+        d = {"years": years.copy()}
+        for k, key in enumerate(KEYS):
+            d[key] = per_cell[i, k]
+        out[name] = d
+    return out
+
+
+def run_help_allcells(cellparams: dict, ncore=None) -> dict:
+    """Run HELP in batch for multiple cells (reference pyhelp/processing.py:40-59)."""
+    tstart = time.perf_counter()
+    if len(cellparams) == 0:
+        return {}
+    batch = batch_from_cellparams(cellparams)
+    res = run_batch(batch, monthly=True)
+    output = split_by_cell(batch, res)
+    print("\nTask completed in %0.2f sec" % (time.perf_counter() - tstart))
+    return output
+
+
+def run_help_singlecell(item):
+    """Run HELP for a single cell (reference pyhelp/processing.py:30-37)."""
+    cellname, outparam = item
+    out = run_help_allcells({cellname: outparam})
+    return (cellname, out[cellname])
+
+
+def post_process_output(output: dict, context=None, lat_dd=None, lon_dd=None) -> dict:
+    """``HelpManager._post_process_output`` (reference pyhelp/managers.py:448-506):
+    per-cell dicts -> the ``HelpOutput.data`` layout, (Np, Ny, 12) float64 arrays,
+    recharge of ``context == 2`` cells redistributed to subsurface runoff."""
+    cellnames = list(output.keys())
+    years = output[cellnames[0]]["years"]
+    Np, Ny = len(cellnames), len(years)
+    keys = ["precip", "runoff", "evapo", "perco", "subrun1", "subrun2", "rechg"]
+    data = {key: np.zeros((Np, Ny, 12)) for key in keys}
+    data["cid"] = cellnames
+    data["years"] = years
+    data["idx_nan"] = []
+    if lat_dd is not None:
+        data["lat_dd"] = np.asarray(lat_dd)
+    if lon_dd is not None:
+        data["lon_dd"] = np.asarray(lon_dd)
+    ctx = [0] * Np if context is None else list(context)
+    for i, cellname in enumerate(cellnames):
+        o = output[cellname]
+        for key in keys[:-1]:
+            data[key][i, :, :] = o[key]
+        if np.any(np.isnan(o["rechg"])):
+            data["idx_nan"].append(i)
+            data["rechg"][i, :, :] = o["rechg"]
+        elif ctx[i] == 2:
+            if np.all(o["subrun2"] == 0):
+                data["subrun1"][i, :, :] += o["rechg"]
+            else:
+                data["subrun2"][i, :, :] += o["rechg"]
+        else:
+            data["rechg"][i, :, :] = o["rechg"]
+    return data

@@ -6,6 +6,10 @@ produced by HELP 3.07 (1997, REAL*4 conductivities); PyHELP's HELP3O.FOR holds
 them in REAL*8, and its own acceptance is 0.1 in/yr
 (pyhelp/tests/test_help3o.py:87-118), so agreement is at printed precision on
 most days, not bitwise.  Tolerances below are the measured envelope + margin.
+
+Both builds of the oracle are pinned: "det" (deterministic transcendentals shared
+with the GPU engine, pyhelp_b200/csrc/help_math.h) and "glibc" (the host libm a
+gfortran build of the reference would link).
 """
 import json
 import os.path as osp
@@ -18,13 +22,13 @@ from oracle import oracle
 MM2IN = 0.0393701
 
 
-@pytest.fixture(scope="module")
-def rcra(rcra_dir):
+@pytest.fixture(scope="module", params=["det", "glibc"])
+def rcra(rcra_dir, request):
     d10 = np.char.ljust(open(osp.join(rcra_dir, "RCRA.D10")).read().splitlines(), 80).astype("S80")
     d11 = np.char.ljust(open(osp.join(rcra_dir, "RCRA.D11")).read().splitlines(), 80).astype("S80")
     out = oracle.run_simulation(
         osp.join(rcra_dir, "RCRA.D4"), osp.join(rcra_dir, "RCRA.D7"), osp.join(rcra_dir, "RCRA.D13"),
-        d11, d10, None, 0, 1, 0, 0, 3, 32.0, daily=True)
+        d11, d10, None, 0, 1, 0, 0, 3, 32.0, daily=True, libm=request.param)
     gold = json.load(open(osp.join(rcra_dir, "rcra_expected.json")))
     return out, gold
 
