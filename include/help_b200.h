@@ -159,6 +159,10 @@ void help_b200_engine_destroy(help_b200_engine* e);
 /* ---- misc ------------------------------------------------------------------ */
 int help_b200_abi_version(void);
 int help_b200_device_count(void);
+/* select the CUDA device later help_b200_run / engine_create calls of this thread use
+ * (one process per GPU: pass LOCAL_RANK).  The reference picks its workers with
+ * multiprocessing.Pool(ncore) (pyhelp/processing.py:43-47).                    */
+int help_b200_set_device(int device);
 const char* help_b200_last_error(void);
 /* algorithmic bytes one simulate() moves:
  * 12*W*D + (56+36*L)*N + 336*N*Y, W = distinct nodes referenced, D = days     */
@@ -166,7 +170,8 @@ double help_b200_algorithmic_bytes(const help_b200_batch* batch);
 
 /* diagnostic: evaluate on the device the transcendental function `fn` the engine uses
  * (pyhelp_b200/csrc/help_math.h; 0 pow(x,y) 1 exp 2 log 3 sin 4 cos 5 atan, 6..17 the REAL*4
- * wrappers acos tan pow exp log sin cos log10 sqrt x**8 x**7 x**4) for n host values.  The
+ * wrappers acos tan pow exp log sin cos log10 sqrt x**8 x**7 x**4, 18 the dual-issue pow)
+ * for n host values.  The
  * reference's `**`, EXP, ALOG ... resolve to libm (HELP3O.FOR:1307-1340, 4329-4480); this lets
  * a test prove the device functions return the same bits as the CPU oracle's.               */
 int help_b200_math_eval(int fn, const double* x, const double* y, double* out, int64_t n);

@@ -2336,6 +2336,9 @@ extern "C" int help_oracle_math_eval(int fn, const double* x, const double* y, d
       case 15: r = R4_POW8(af); break;
       case 16: r = R4_POW7(af); break;
       case 17: r = R4_POW4(af); break;
+#ifndef HELP_ORACLE_GLIBC
+      case 18: { double r0, r1; helpmath::det_pow2(a, b, b == 0.0 ? 1.5 : 1.0 / b, a, r0, r1); r = r0; break; }   // dual-issue form
+#endif
       default: return -1;
     }
     out[i] = r;

@@ -14,7 +14,7 @@ import os.path as osp
 import numpy as np
 
 _HERE = osp.dirname(osp.abspath(__file__))
-LIB_PATH = osp.join(_HERE, "libhelp_b200.so")
+LIB_PATH = os.environ.get("HELP_B200_LIB") or osp.join(_HERE, "libhelp_b200.so")   # (override: developer A/B builds)
 
 # enums of include/help_b200.h
 (HB_ULAT, HB_ULAI, HB_EDEPTH, HB_WIND, HB_HUM1, HB_HUM2, HB_HUM3, HB_HUM4, HB_OSNO, HB_FRUNOF,
@@ -91,6 +91,8 @@ def lib():
                                            C.POINTER(C.c_int32)]
     L.help_b200_engine_destroy.restype = None
     L.help_b200_engine_destroy.argtypes = [C.c_void_p]
+    L.help_b200_set_device.restype = C.c_int
+    L.help_b200_set_device.argtypes = [C.c_int]
     L.help_b200_math_eval.restype = C.c_int
     L.help_b200_math_eval.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
     if L.help_b200_abi_version() != 1:
@@ -108,6 +110,10 @@ def check(rc: int, what: str):
 def require_device():
     if lib().help_b200_device_count() < 1:
         raise EngineError("no CUDA device visible: the HELP engine runs on the GPU only (no CPU fallback)")
+
+
+def set_device(index: int):
+    check(lib().help_b200_set_device(int(index)), "set_device")
 
 
 def ptr(a: np.ndarray | None):

@@ -37,17 +37,18 @@ def needs_build() -> bool:
     return any(osp.getmtime(osp.join(SRC, d)) > t for d in DEPS)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if force or needs_build():
+def build(force: bool = False, verbose: bool = False, out: str | None = None, defines=()) -> str:
+    """Compile the engine.  `out`/`defines` are for developer A/B builds (scripts/)."""
+    if force or out or needs_build():
         cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-            ["-o", OUT] + [osp.join(SRC, s) for s in SOURCES]
+            ["-D" + d for d in defines] + ["-o", out or OUT] + [osp.join(SRC, s) for s in SOURCES]
         env = dict(os.environ)
         r = subprocess.run(cmd, cwd=SRC, env=env, capture_output=True, text=True)
         if verbose:
             sys.stderr.write(r.stderr)
         if r.returncode != 0:
             raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
-    return OUT
+    return out or OUT
 
 
 if __name__ == "__main__":

@@ -141,6 +141,12 @@ extern "C" int help_b200_device_count(void) {
   return n;
 }
 
+extern "C" int help_b200_set_device(int device) {
+  if (device < 0 || device >= help_b200_device_count()) return fail(HELP_B200_ENODEV, "set_device: no such CUDA device");
+  CU(cudaSetDevice(device));
+  return 0;
+}
+
 extern "C" int help_b200_engine_create(const help_b200_batch* b, int want_monthly, int want_raw,
                                        help_b200_engine** out) {
   if (!out) return fail(HELP_B200_EINVAL, "out is NULL");
@@ -182,7 +188,7 @@ extern "C" int help_b200_engine_create(const help_b200_batch* b, int want_monthl
   TRY(dev_alloc(&e->d_layer_rc, (size_t)ml * n));
   TRY(dev_alloc(&e->d_img_f32, (size_t)Image::n_f32(e->segcap) * e->stride));
   TRY(dev_alloc(&e->d_img_i32, (size_t)Image::n_i32(e->segcap) * e->stride));
-  TRY(dev_alloc(&e->d_img_f64, (size_t)Image::n_f64() * e->stride));
+  TRY(dev_alloc(&e->d_img_f64, (size_t)Image::n_f64(e->segcap) * e->stride));
   if (e->want_monthly) TRY(dev_alloc(&e->d_monthly, (size_t)HR_NROWS * ny * 12 * n));
   if (e->want_raw) TRY(dev_alloc(&e->d_raw, (size_t)HELP_B200_RAW_ROWS * ny * 12 * n));
   TRY(dev_alloc(&e->d_yearly, (size_t)HY_NROWS * ny * n));
@@ -238,7 +244,7 @@ extern "C" int help_b200_engine_create(const help_b200_batch* b, int want_monthl
 
 template <int MAXSEG>
 static void launch_sim(const SimArgs& A, int64_t n, cudaStream_t st) {
-  const int th = 64;
+  const int th = HELP_SIM_THREADS;
   help_sim_kernel<MAXSEG><<<(unsigned)((n + th - 1) / th), th, 0, st>>>(A);
 }
 
@@ -354,13 +360,14 @@ __global__ void math_eval_kernel(int fn, const double* __restrict__ x, const dou
     case 15: r = r4_pow8(af); break;
     case 16: r = r4_pow7(af); break;
     case 17: r = r4_pow4(af); break;
+    case 18: { double r0, r1; helpmath::det_pow2(a, b, b == 0.0 ? 1.5 : 1.0 / b, a, r0, r1); r = r0; break; }
     default: break;
   }
   out[i] = r;
 }
 
 extern "C" int help_b200_math_eval(int fn, const double* x, const double* y, double* out, int64_t n) {
-  if (fn < 0 || fn > 17 || !x || !out || n < 0) return fail(HELP_B200_EINVAL, "math_eval: bad argument");
+  if (fn < 0 || fn > 18 || !x || !out || n < 0) return fail(HELP_B200_EINVAL, "math_eval: bad argument");
   if (help_b200_device_count() < 1) return fail(HELP_B200_ENODEV, "no CUDA device (this engine has no CPU path)");
   if (n == 0) return 0;
   double *dx = nullptr, *dy = nullptr, *d_out = nullptr;

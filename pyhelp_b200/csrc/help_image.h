@@ -68,7 +68,19 @@ enum ImgSF : int {
   S_RC,          // RCUL     saturated K, in/day
   S_SUBIN,       // SUBINS   subsurface inflow, in/day
   S_SW0,         // SWUL     initial storage
+  S_RELMIN,      // REAL*4 (WPUL - RSUL)/(UL - RSUL): RELMIN of F:4329, a constant of the segment
   S_NF
+};
+// ---- f64 per segment: constants of the routing loop that cost a division or a pow ---------------
+// Each is the value the reference's expression takes (same operations, same order), hoisted
+// out of the sub-step loop because it depends only on the segment and on DT = 1/NSTEP(n).
+enum ImgSD : int {
+  SD_C = 0,      // 3 + 2/lambda                                   (F:4420, 4465)
+  SD_NIL,        // -1/lambda                                      (F:4334, 4360)
+  SD_BC,         // B = K dt (1/(UL-RS))**C of the Newton solve     (F:4466)
+  SD_LOWWP,      // LOW = K dt ((WP-RS)/(UL-RS))**C, i.e. SWLIM = WP (F:4420)
+  SD_LOWFC,      // LOW at SWLIM = FC
+  SD_NF
 };
 // ---- f64 per subprofile ---------------------------------------------------------
 enum ImgPD : int {
@@ -93,7 +105,7 @@ enum ImgPI : int {
   Q_LD,          // LD(n)
   Q_NF
 };
-// i32 per segment: bit0 = LAYSEG(J,2) < LD(NPROF) (F:4494,4499)
+// i32 per segment: bit0 = LAYSEG(J,2) < LD(NPROF) (F:4494), bit1 = the same for J+1 (F:4499)
 
 struct Image {
   float* f32;
@@ -104,7 +116,7 @@ struct Image {
 
   __host__ __device__ static int64_t n_f32(int segcap) { return F_NSCALAR + P_NF * kNProf + (int64_t)S_NF * segcap; }
   __host__ __device__ static int64_t n_i32(int segcap) { return I_NSCALAR + Q_NF * kNProf + segcap; }
-  __host__ __device__ static int64_t n_f64() { return D_NF * kNProf; }
+  __host__ __device__ static int64_t n_f64(int segcap) { return D_NF * kNProf + (int64_t)SD_NF * segcap; }
 
   __device__ __forceinline__ float& F(int f, int64_t c) const { return f32[(int64_t)f * stride + c]; }
   __device__ __forceinline__ float& PF(int f, int n, int64_t c) const {   // n = 1..6
@@ -122,6 +134,9 @@ struct Image {
   }
   __device__ __forceinline__ double& PD(int f, int n, int64_t c) const {
     return f64[(int64_t)(f * kNProf + (n - 1)) * stride + c];
+  }
+  __device__ __forceinline__ double& SD(int f, int j, int64_t c) const {   // j = 1..segcap
+    return f64[(int64_t)(D_NF * kNProf + f * segcap + (j - 1)) * stride + c];
   }
 };
 
@@ -141,6 +156,9 @@ using helpmath::r4_exp; using helpmath::r4_log; using helpmath::r4_log10; using 
 using helpmath::r4_cos; using helpmath::r4_tan; using helpmath::r4_acos; using helpmath::r4_pow;
 using helpmath::r4_sqrt; using helpmath::r4_pow8; using helpmath::r4_pow7; using helpmath::r4_pow4;
 __host__ __device__ __forceinline__ double r8_pow(double x, double y) { return helpmath::det_pow(x, y); }
+__host__ __device__ __forceinline__ void r8_pow2(double x0, double y0, double x1, double y1, double& r0, double& r1) {
+  helpmath::det_pow2(x0, y0, x1, y1, r0, r1);   // two independent powers, same bits as r8_pow
+}
 __host__ __device__ __forceinline__ double r8_log(double x) { return helpmath::det_log(x); }
 __host__ __device__ __forceinline__ double r8_atan(double x) { return helpmath::det_atan(x); }
 __host__ __device__ __forceinline__ double r8_sin(double x) { return helpmath::det_sin(x); }

@@ -650,6 +650,33 @@ help_setup_kernel(BatchDev B, Image img, const int32_t* __restrict__ perm, uint3
     img.SF(S_SUBIN, J, slot) = in ? DSUBINd[J] : 0.f;  img.SF(S_SW0, J, slot) = in ? S.SWUL[J] : 0.f;
     if (!in) img.SI(J, slot) = 0;
   }
+  // ---- routing-loop constants per segment (help_image.h ImgSD; F:4329, 4420, 4465-4466) -------------
+  {
+    int N = 1, eseg = S.NSEGn[1];
+    for (int J = 1; J <= img.segcap; ++J) {
+      while (N < 6 && J > eseg) { ++N; eseg += S.NSEGn[N]; }
+      const bool in = (J <= S.NSEG);
+      double C = 0.0, nil = 0.0, bc = 0.0, lowwp = 0.0, lowfc = 0.0;
+      float relmin = 0.f;
+      if (in) {
+        const double DT = 1.0 / (double)T.NSTEP[N];
+        const double ul = (double)S.UL[J], rs = (double)S.RSUL[J], lam = (double)S.XLAMBU[J];
+        const double wp = (double)S.WPUL[J], fc = (double)S.FCUL[J];
+        const double span = ul - rs;
+        const double kdt = (double)S.RCUL[J] * DT;
+        C = 3.0 + (2.0 / lam);
+        nil = -1.0 / lam;
+        relmin = (float)((wp - rs) / span);
+        bc = kdt * r8_pow(1.0 / span, C);
+        lowwp = kdt * r8_pow((wp - rs) / span, C);
+        lowfc = kdt * r8_pow((fc - rs) / span, C);
+      }
+      img.SF(S_RELMIN, J, slot) = relmin;
+      img.SD(SD_C, J, slot) = C; img.SD(SD_NIL, J, slot) = nil; img.SD(SD_BC, J, slot) = bc;
+      img.SD(SD_LOWWP, J, slot) = lowwp; img.SD(SD_LOWFC, J, slot) = lowfc;
+    }
+    for (int J = 1; J < img.segcap; ++J) img.SI(J, slot) = (img.SI(J, slot) & 1) | ((img.SI(J + 1, slot) & 1) << 1);
+  }
   const int hemi = (C.ULAT >= 0.0f) ? 0 : 1;
   const int IDFS = B.idfs[(int64_t)node_r * 2 + hemi];
   img.I(I_NSEG, slot) = S.NSEG; img.I(I_IPL, slot) = C.IPL; img.I(I_IHV, slot) = C.IHV; img.I(I_IDFS, slot) = IDFS;

@@ -64,19 +64,6 @@ __device__ __forceinline__ float f73(float v, uint32_t& flag) {
 // last julian day of each month in a non-leap year (MONTH, F:1073)
 __constant__ int kICAL[13] = {0, 31, 59, 90, 120, 151, 181, 212, 243, 273, 304, 334, 365};
 
-struct SegC { double ul, fc, wp, rs, lam, bub, rc, th, sub; int above; };
-
-__device__ __forceinline__ SegC load_seg(const Image& img, int j, int64_t s) {
-  SegC c;
-  c.ul = (double)__ldg(&img.SF(S_UL, j, s));   c.fc = (double)__ldg(&img.SF(S_FC, j, s));
-  c.wp = (double)__ldg(&img.SF(S_WP, j, s));   c.rs = (double)__ldg(&img.SF(S_RS, j, s));
-  c.lam = (double)__ldg(&img.SF(S_LAM, j, s)); c.bub = (double)__ldg(&img.SF(S_BUB, j, s));
-  c.rc = (double)__ldg(&img.SF(S_RC, j, s));   c.th = (double)__ldg(&img.SF(S_THICK, j, s));
-  c.sub = (double)__ldg(&img.SF(S_SUBIN, j, s));
-  c.above = __ldg(&img.SI(j, s));
-  return c;
-}
-
 // ---- geomembrane leakage (FML, F:4870-5304) ------------------------------------
 struct FmlC { int lcase, lpq, ltype; float thklin, phole, defec, trans; double rclin, rcs, dth; };
 
@@ -218,16 +205,59 @@ __device__ __noinline__ double lateral_rate(const Image& img, int64_t s, int NSE
 // ---- one subprofile, one day (DRAIN/AVROUT/PROFIL/HEAD, F:4133-4617) ------------------
 // SW/BAL: per-segment state (1-based).  DRIN: scratch, DRIN[j] = inflow into segment j.
 // ET7[1..7]: today's evapotranspiration demand per evaporative segment (inches).
+// SWLc/LOWc: scratch of the capillary pre-pass (below).
 struct ProfC {
   int n, NSEGB, NSEGE, NSEG, nstep, ibar, lat;
   float drculs, dthics, slope, xleng, sublin;
   FmlC fml;
 };
 
+// Lower storage limit of segment J when it is in capillary equilibrium with the segment
+// below (F:4330-4340 == F:4356-4366) and the unrestricted drainage LOW at that limit
+// (F:4420-4421).  Both depend only on the state of J+1 at the start of the sub-step, so every
+// segment's pair is independent of the top-down routing order: the pre-pass evaluates them
+// for all segments of all 32 cells of a warp in lockstep, TWO segments per iteration through
+// the dual-issue power r8_pow2 (three powers per segment: psi, relative storage, LOW).
+struct CapIn {
+  double rs1, ul1, bub1, nil1, bub, lam, span, rs, wp, fc, kdt, C;
+  float relmin1;
+};
+__device__ __forceinline__ CapIn cap_load(const Image& img, int64_t s, int J, double DT) {
+  CapIn c;
+  c.rs1 = (double)__ldg(&img.SF(S_RS, J + 1, s)); c.ul1 = (double)__ldg(&img.SF(S_UL, J + 1, s));
+  c.bub1 = (double)__ldg(&img.SF(S_BUB, J + 1, s)); c.relmin1 = __ldg(&img.SF(S_RELMIN, J + 1, s));
+  c.nil1 = __ldg(&img.SD(SD_NIL, J + 1, s));
+  c.bub = (double)__ldg(&img.SF(S_BUB, J, s)); c.lam = (double)__ldg(&img.SF(S_LAM, J, s));
+  const double ul = (double)__ldg(&img.SF(S_UL, J, s));
+  c.rs = (double)__ldg(&img.SF(S_RS, J, s)); c.span = ul - c.rs;
+  c.wp = (double)__ldg(&img.SF(S_WP, J, s)); c.fc = (double)__ldg(&img.SF(S_FC, J, s));
+  c.kdt = (double)__ldg(&img.SF(S_RC, J, s)) * DT; c.C = __ldg(&img.SD(SD_C, J, s));
+  return c;
+}
+__device__ __forceinline__ float cap_relsw(const CapIn& c, double base1) {
+  float RELSW = (float)((base1 - c.rs1) / (c.ul1 - c.rs1));
+  if (RELSW < c.relmin1) RELSW = c.relmin1;
+  return RELSW;
+}
+__device__ __forceinline__ double cap_ratio(const CapIn& c, double psi_pow) {     // BUB(J)/PSIJP1
+  float PSIJP1 = (float)(c.bub1 * psi_pow);
+  if ((double)PSIJP1 < c.bub) PSIJP1 = (float)c.bub;
+  return c.bub / (double)PSIJP1;
+}
+__device__ __forceinline__ float cap_swlim(const CapIn& c, double rel_pow) {
+  const float RELSWL = (float)rel_pow;
+  float SWLIM = (float)(((double)RELSWL * c.span) + c.rs);
+  if ((double)SWLIM < c.wp) SWLIM = (float)c.wp;
+  if ((double)SWLIM > c.fc) SWLIM = (float)c.fc;
+  return SWLIM;
+}
+
+template <int MAXSEG>
 __device__ __noinline__ void route_subprofile(const Image& img, int64_t s, const ProfC& P, float FIN,
                                               const float* __restrict__ ET7, int IFREZ,
                                               double* __restrict__ SW, double* __restrict__ BAL,
-                                              double* __restrict__ DRIN, double& DRNo, double& PRCo,
+                                              double* __restrict__ DRIN, float* __restrict__ SWLc,
+                                              double* __restrict__ LOWc, double& DRNo, double& PRCo,
                                               float& EXTRA, uint32_t& flag) {
   const int NSEGB = P.NSEGB, NSEGE = P.NSEGE, NSEG = P.NSEG, IBAR = P.ibar, LAT = P.lat;
   const int NSEGL = (IBAR == 0 || IBAR == 3) ? NSEGE : NSEGE - 1;
@@ -263,52 +293,66 @@ __device__ __noinline__ void route_subprofile(const Image& img, int64_t s, const
         if (LAT == 1) QLATY = lateral_rate(img, s, NSEGB, NSEGL, THY, P.slope, P.xleng);
       }
     }
-    // AVROUT (F:4287-4527): top -> bottom
-    bool routed_bottom = false;
-    SegC c = load_seg(img, NSEGB, s), nx = c;
+    // ---- capillary pre-pass: limits of all segments that can take the capillary branch -------
+    // (J < NSEGL; which of them USE the value is decided in the routing loop below)
+    {
+      int J = NSEGB;
+      for (; J + 1 < NSEGL; J += 2) {
+        const CapIn a = cap_load(img, s, J, DT), b = cap_load(img, s, J + 1, DT);
+        const float ra = cap_relsw(a, SW[J + 1] + (BAL[J + 1] / 2.0)), rb = cap_relsw(b, SW[J + 2] + (BAL[J + 2] / 2.0));
+        double pa, pb;
+        r8_pow2((double)ra, a.nil1, (double)rb, b.nil1, pa, pb);
+        r8_pow2(cap_ratio(a, pa), a.lam, cap_ratio(b, pb), b.lam, pa, pb);
+        const float la = cap_swlim(a, pa), lb = cap_swlim(b, pb);
+        r8_pow2(((double)la - a.rs) / a.span, a.C, ((double)lb - b.rs) / b.span, b.C, pa, pb);
+        SWLc[J] = la; LOWc[J] = a.kdt * pa; SWLc[J + 1] = lb; LOWc[J + 1] = b.kdt * pb;
+      }
+      if (J < NSEGL) {
+        const CapIn a = cap_load(img, s, J, DT);
+        const float ra = cap_relsw(a, SW[J + 1] + (BAL[J + 1] / 2.0));
+        const float la = cap_swlim(a, r8_pow(cap_ratio(a, r8_pow((double)ra, a.nil1)), a.lam));
+        SWLc[J] = la; LOWc[J] = a.kdt * r8_pow(((double)la - a.rs) / a.span, a.C);
+      }
+    }
+    // ---- AVROUT (F:4287-4527): top -> bottom ---------------------------------------------------
     for (int J = NSEGB; J <= NSEGL; ++J) {
-      if (J > NSEGB) c = nx;
-      if (J < NSEGL) nx = load_seg(img, J + 1, s);
+      const double ul = (double)__ldg(&img.SF(S_UL, J, s)), rs = (double)__ldg(&img.SF(S_RS, J, s));
+      const double wp = (double)__ldg(&img.SF(S_WP, J, s)), fc = (double)__ldg(&img.SF(S_FC, J, s));
+      const double kdt = (double)__ldg(&img.SF(S_RC, J, s)) * DT;
       const double Ej = (J <= 7) ? (double)ET7[J] * DT : 0.0;
-      const double DSUBj = c.sub * DT;
-      float SWLIM;
-      bool cap = false;
-      if (J <= 7) { SWLIM = (float)c.wp; if (DRIN[J] == 0.0 && J < NSEGL) cap = true; }
-      else if (J == NSEGL && J != NSEG) SWLIM = (float)c.fc;
-      else if (J == NSEG && DRIN[J] > 0.0) SWLIM = (float)c.wp;
-      else if (J == NSEG && DRIN[J] <= 0.0) SWLIM = (float)c.fc;
-      else cap = true;
-      if (cap) {       // capillary equilibrium with the segment below (F:4330-4340)
-        const float RELMIN = (float)((nx.wp - nx.rs) / (nx.ul - nx.rs));
-        float RELSW = (float)((SW[J + 1] + (BAL[J + 1] / 2.0) - nx.rs) / (nx.ul - nx.rs));
-        if (RELSW < RELMIN) RELSW = RELMIN;
-        float PSIJP1 = (float)(nx.bub * r8_pow((double)RELSW, -1.0 / nx.lam));
-        if ((double)PSIJP1 < c.bub) PSIJP1 = (float)c.bub;
-        const float RELSWL = (float)r8_pow(c.bub / (double)PSIJP1, c.lam);
-        SWLIM = (float)(((double)RELSWL * (c.ul - c.rs)) + c.rs);
-        if ((double)SWLIM < c.wp) SWLIM = (float)c.wp;
-        if ((double)SWLIM > c.fc) SWLIM = (float)c.fc;
-      }
+      const double DSUBj = (double)__ldg(&img.SF(S_SUBIN, J, s)) * DT;
+      const double drin = DRIN[J];
+      // lower storage limit SWLIM and the drainage LOW at that limit; kind: 0 capillary
+      // (pre-pass), 1 wilting point, 2 field capacity, 3 porosity (frozen soil)
+      int kind;
       if (J <= 7) {
-        if (J == NSEGL) SWLIM = (float)c.fc;
-        if (J == NSEG) SWLIM = (float)c.fc;
-        if (J == NSEG && DRIN[J] > 0.0) SWLIM = (float)c.wp;
-        if (IFREZ == 1) SWLIM = (float)c.ul;
-      }
-      const double swl = (double)SWLIM;
+        kind = (drin == 0.0 && J < NSEGL) ? 0 : 1;
+        if (J == NSEGL) kind = 2;
+        if (J == NSEG) kind = 2;
+        if (J == NSEG && drin > 0.0) kind = 1;
+        if (IFREZ == 1) kind = 3;
+      } else if (J == NSEGL && J != NSEG) kind = 2;
+      else if (J == NSEG && drin > 0.0) kind = 1;
+      else if (J == NSEG && drin <= 0.0) kind = 2;
+      else kind = 0;
+      double swl, LOW;
+      if (kind == 0) { swl = (double)SWLc[J]; LOW = LOWc[J]; }
+      else if (kind == 1) { swl = wp; LOW = __ldg(&img.SD(SD_LOWWP, J, s)); }
+      else if (kind == 2) { swl = fc; LOW = __ldg(&img.SD(SD_LOWFC, J, s)); }
+      else { swl = ul; LOW = kdt; }            // ((ul - rs)/(ul - rs))**C == 1
       const double base = SW[J] + (BAL[J] / 2.0);                     // storage at the start of the step
-      double DRNMAX = base + DRIN[J] + DSUBj - Ej - swl;
+      double DRNMAX = base + drin + DSUBj - Ej - swl;
       if (J == NSEGL) {
         if (bottom) {
           if (IBAR == 3) DRNMAX = 0.0;
           if (IBAR > 3) DRNMAX = DRNMAX + DSUBE;
           if (IBAR >= 3) {
             DRIN[NSEGE + 1] = 0.0;
-            if (LAT == 0) { DRIN[NSEGL + 1] = 0.0; routed_bottom = true; break; }
+            if (LAT == 0) { DRIN[NSEGL + 1] = 0.0; break; }
           }
         }
         if (liner) {    // split the gravity water between leakage and lateral flow (F:4384-4413)
-          double GRVWAT = DRNMAX + swl - c.fc;
+          double GRVWAT = DRNMAX + swl - fc;
           if (GRVWAT <= 0.0) {
             DRIN[NSEGE + 1] = 0.0; DRIN[NSEGL + 1] = 0.0;
             if (IBAR < 3) DRIN[NSEGE + 1] = DRIN[NSEGE + 1] + DSUBE;
@@ -325,39 +369,37 @@ __device__ __noinline__ void route_subprofile(const Image& img, int64_t s, const
             }
             if (IBAR < 3) DRIN[NSEGE + 1] = DRIN[NSEGE + 1] + DSUBE;
           }
-          routed_bottom = true;
           break;
         }
       }
       if (DRNMAX < 0.0) DRNMAX = 0.0;
-      const double span = c.ul - c.rs;
-      const double C = 3.0 + (2.0 / c.lam);
-      const double kdt = c.rc * DT;
+      const double span = ul - rs;
       const bool add_sub = (J == NSEGL && bottom && IBAR > 3);
       double out;
-      double LOW = kdt * r8_pow((swl - c.rs) / span, C);
       if (LOW > DRNMAX) out = DRNMAX;
       else {
-        double SWMAX = base + DSUBj + DRIN[J] - Ej;
+        double SWMAX = base + DSUBj + drin - Ej;
         if (add_sub) SWMAX = SWMAX + DSUBE;
-        if (SWMAX > c.ul) SWMAX = c.ul;
+        if (SWMAX > ul) SWMAX = ul;
         if (SWMAX <= swl) out = 0.0;
         else {
-          double HIGH = kdt * r8_pow((SWMAX - c.rs) / span, C);
+          const double C = __ldg(&img.SD(SD_C, J, s));
+          double HIGH = kdt * r8_pow((SWMAX - rs) / span, C);
           if (HIGH > DRNMAX) HIGH = DRNMAX;
           double SWMIN = SWMAX - HIGH;
           if (SWMIN < swl) SWMIN = swl;
-          LOW = kdt * r8_pow((SWMIN - c.rs) / span, C);
+          LOW = kdt * r8_pow((SWMIN - rs) / span, C);
           if (LOW > DRNMAX) LOW = DRNMAX;
-          SWMAX = base + DSUBj + DRIN[J] - Ej - LOW;
+          SWMAX = base + DSUBj + drin - Ej - LOW;
           if (add_sub) SWMAX = SWMAX + DSUBE;
-          if (SWMAX > c.ul) SWMAX = c.ul;
+          if (SWMAX > ul) SWMAX = ul;
           if (SWMAX <= SWMIN) out = DRNMAX;
           else {
-            // Newton on f(x) = A - B x^C - 2x (F:4461-4488)
-            double A = 2.0 * (SW[J] - c.rs) + BAL[J] + DRIN[J] + DSUBj - Ej;
+            // Newton on f(x) = A - B x^C - 2x (F:4461-4488); B = K dt (1/(ul-rs))^C is a
+            // constant of the segment (set-up kernel)
+            double A = 2.0 * (SW[J] - rs) + BAL[J] + drin + DSUBj - Ej;
             if (add_sub) A = A + (2.0 * DSUBE);
-            const double Bc = kdt * r8_pow(1.0 / span, C);
+            const double Bc = __ldg(&img.SD(SD_BC, J, s));
             const double TOLER = 0.003 * span;
             const double ftol = (double)0.3f * TOLER;
             double X0 = (SWMAX + SWMIN) / 2.0;
@@ -374,21 +416,24 @@ __device__ __noinline__ void route_subprofile(const Image& img, int64_t s, const
             if (ITER > 100) flag |= kFlagNonConv;
             if (X0 > SWMAX) X0 = SWMAX;
             if (X0 < SWMIN) X0 = SWMIN;
-            out = 2.0 * (SW[J] - X0) + BAL[J] + DRIN[J] + DSUBj - Ej;
+            out = 2.0 * (SW[J] - X0) + BAL[J] + drin + DSUBj - Ej;
             if (bottom && IBAR > 3) out = out + DSUBE;
           }
         }
       }
-      if (c.above) { if (out > kdt) out = kdt; }
+      const int above = __ldg(&img.SI(J, s));       // bit0: J above the drain layer, bit1: J+1 is
+      if (above & 1) { if (out > kdt) out = kdt; }
       if (out > DRNMAX) out = DRNMAX;
       if (out < 0.0) out = 0.0;
-      if (J < NSEGL && nx.above) {
-        const double kdt1 = nx.rc * DT;
+      if (J < NSEGL && (above & 2)) {
+        const double kdt1 = (double)__ldg(&img.SF(S_RC, J + 1, s)) * DT;
         if (out > kdt1) {
-          const float sw = (float)((base - c.rs) / span);
-          const float TRATIO = (float)(c.th / nx.th);
+          const double th = (double)__ldg(&img.SF(S_THICK, J, s)), th1 = (double)__ldg(&img.SF(S_THICK, J + 1, s));
+          const double ul1 = (double)__ldg(&img.SF(S_UL, J + 1, s)), sub1 = (double)__ldg(&img.SF(S_SUBIN, J + 1, s));
+          const float sw = (float)((base - rs) / span);
+          const float TRATIO = (float)(th / th1);
           const double En = (J + 1 <= 7) ? (double)ET7[J + 1] * DT : 0.0;
-          double DRMX = nx.ul - SW[J + 1] - (BAL[J + 1] / 2.0) + kdt1 + En - nx.sub * DT;
+          double DRMX = ul1 - SW[J + 1] - (BAL[J + 1] / 2.0) + kdt1 + En - sub1 * DT;
           if (DRMX > DRNMAX) DRMX = DRNMAX;
           double DRNMX = kdt1 * (double)(1.0f + (sw * TRATIO));
           if (DRNMX > DRMX) DRNMX = DRMX;
@@ -398,11 +443,7 @@ __device__ __noinline__ void route_subprofile(const Image& img, int64_t s, const
         }
       }
       DRIN[J + 1] = out;
-#ifdef HELP_DBG_SEG
-      HELP_DBG_SEG
-#endif
     }
-    (void)routed_bottom;
     // F:4518-4525 and PROFIL (F:4535-4574) fused: new balance bottom -> top, pushing
     // water above saturation into the segment above
     if (IBAR == 3) DRIN[NSEGE + 1] = 0.0;
@@ -462,8 +503,14 @@ struct Surf {      // REAL*4 surface-process state of one cell
   float RAIN, SMELT, GMRO, ADDRUN, RUN, PINF, ETT, ESS, EP, ES, ETO, ABST, ET[8];
 };
 
+#ifndef HELP_SIM_THREADS
+#define HELP_SIM_THREADS 64
+#endif
+#ifndef HELP_SIM_MINBLOCKS
+#define HELP_SIM_MINBLOCKS 12
+#endif
 template <int MAXSEG>
-__global__ void __launch_bounds__(64) help_sim_kernel(SimArgs A) {
+__global__ void __launch_bounds__(HELP_SIM_THREADS, HELP_SIM_MINBLOCKS) help_sim_kernel(SimArgs A) {
   const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= A.n_cells) return;
   const Image& img = A.img;
@@ -531,7 +578,8 @@ __global__ void __launch_bounds__(64) help_sim_kernel(SimArgs A) {
     }
   }
   // ---- state (run_simulation F:200-317; READIN F:1344-1351; INITIA F:2437-2442) ---------------
-  double SW[MAXSEG + 2], BAL[MAXSEG + 2], DRIN[MAXSEG + 3];
+  double SW[MAXSEG + 2], BAL[MAXSEG + 2], DRIN[MAXSEG + 3], LOWc[MAXSEG + 2];
+  float SWLc[MAXSEG + 2];
   for (int J = 1; J <= NSEG; ++J) { SW[J] = (double)img.SF(S_SW0, J, s); BAL[J] = 0.0; }
   SW[0] = BAL[0] = 0.0; SW[NSEG + 1] = BAL[NSEG + 1] = 0.0;
   Surf U;
@@ -1116,7 +1164,7 @@ __global__ void __launch_bounds__(64) help_sim_kernel(SimArgs A) {
 #ifdef HELP_DBG_PRE
         HELP_DBG_PRE
 #endif
-        route_subprofile(img, s, PR[1], U.PINF, U.ET, U.IFREZ, SW, BAL, DRIN, DRN[1], PRC[1], U.ADDRUN, flag);
+        route_subprofile<MAXSEG>(img, s, PR[1], U.PINF, U.ET, U.IFREZ, SW, BAL, DRIN, SWLc, LOWc, DRN[1], PRC[1], U.ADDRUN, flag);
         {
           float EXET = 0.0f;
 #pragma unroll
@@ -1149,7 +1197,7 @@ __global__ void __launch_bounds__(64) help_sim_kernel(SimArgs A) {
           const float FINn = (float)(PRC[N - 1] + (double)EXWAT[N]);
           if (N > nprof) break;
           EXWAT[N] = 0.0f;
-          route_subprofile(img, s, PR[N], FINn, U.ET, U.IFREZ, SW, BAL, DRIN, DRN[N], PRC[N], EXWAT[N], flag);
+          route_subprofile<MAXSEG>(img, s, PR[N], FINn, U.ET, U.IFREZ, SW, BAL, DRIN, SWLc, LOWc, DRN[N], PRC[N], EXWAT[N], flag);
           if (N <= 5) {
             if (LDn[N] > 0) {
               const double RCR = (double)RECIR[N] * DRN[N] / (double)100.0f;

@@ -123,6 +123,7 @@ def run_help_allcells(cellparams: dict, ncore=None) -> dict:
     tstart = time.perf_counter()
     if len(cellparams) == 0:
         return {}
+    N.require_device()          # fail before any host work: this path has no CPU fallback
     batch = batch_from_cellparams(cellparams)
     res = run_batch(batch, monthly=True)
     output = split_by_cell(batch, res)

@@ -13,7 +13,7 @@
 #define __noinline__
 #define __restrict__
 #define __constant__ static const
-#define __launch_bounds__(x)
+#define __launch_bounds__(...)
 struct dim3s { unsigned x, y, z; };
 static thread_local dim3s blockIdx{0, 0, 0}, threadIdx{0, 0, 0}, blockDim{1, 1, 1}, gridDim{1, 1, 1};
 template <typename T> static inline T __ldg(const T* p) { return *p; }
@@ -37,5 +37,32 @@ static inline float r4_sqrt(float x) { return powf(x, 0.5f); }
 static inline float r4_pow8(float x) { return powf(x, 8.f); }
 static inline float r4_pow7(float x) { return powf(x, 7.f); }
 static inline float r4_pow4(float x) { return powf(x, 4.f); }
+static inline double r8_pow(double x, double y) { return pow(x, y); }
+static inline void r8_pow2(double x0, double y0, double x1, double y1, double& r0, double& r1) { r0 = pow(x0, y0); r1 = pow(x1, y1); }
+static inline double r8_log(double x) { return log(x); }
+static inline double r8_atan(double x) { return atan(x); }
+static inline double r8_sin(double x) { return sin(x); }
+static inline double r8_cos(double x) { return cos(x); }
+static inline double r8_sqrt(double x) { return sqrt(x); }
 }
+#endif
+
+#ifdef HELP_EMU_COUNT   // count r8_pow calls per source line (where do the pows go?)
+#define HELP_R4_OVERRIDE
+#include "../../pyhelp_b200/csrc/help_math.h"
+static long long g_pow_count[4096];
+namespace helpb200 {
+using helpmath::r4_exp; using helpmath::r4_log; using helpmath::r4_log10; using helpmath::r4_sin;
+using helpmath::r4_cos; using helpmath::r4_tan; using helpmath::r4_acos; using helpmath::r4_pow;
+using helpmath::r4_sqrt; using helpmath::r4_pow8; using helpmath::r4_pow7; using helpmath::r4_pow4;
+static inline double r8_log(double x) { return helpmath::det_log(x); }
+static inline double r8_atan(double x) { return helpmath::det_atan(x); }
+static inline double r8_sin(double x) { return helpmath::det_sin(x); }
+static inline double r8_cos(double x) { return helpmath::det_cos(x); }
+static inline double r8_sqrt(double x) { return helpmath::hm_sqrt(x); }
+}
+static long long g_cap[8]; static float g_prev_relsw[128];
+#define HELP_DBG_CAP { g_cap[0]++; if (RELSW == RELMIN) g_cap[1]++; if ((double)PSIJP1 == c.bub) g_cap[2]++; if ((double)SWLIM == c.wp) g_cap[3]++; if ((double)SWLIM == c.fc) g_cap[4]++; if (RELSW == g_prev_relsw[J]) g_cap[5]++; g_prev_relsw[J] = RELSW; }
+#define r8_pow(x, y) (g_pow_count[__LINE__ & 4095]++, helpmath::det_pow(x, y))
+#define r8_pow2(x0, y0, x1, y1, r0, r1) (g_pow_count[__LINE__ & 4095] += 2, helpmath::det_pow2(x0, y0, x1, y1, r0, r1))
 #endif

@@ -29,7 +29,7 @@ extern "C" int emu_run(const help_b200_batch* b, float* monthly, float* yearly, 
   B.tm_normals = b->tm_normals; B.idfs = b->idfs; B.cell_f32 = b->cell_f32; B.cell_i32 = b->cell_i32; B.layer_f32 = b->layer_f32; B.layer_i32 = b->layer_i32; B.layer_rc = b->layer_rc;
   int segcap = 7 + 3 * b->max_layers; if (segcap > 67) segcap = 67;
   int64_t stride = ((n + 31) / 32) * 32;
-  std::vector<float> f32(Image::n_f32(segcap) * stride); std::vector<int32_t> i32(Image::n_i32(segcap) * stride); std::vector<double> f64(Image::n_f64() * stride);
+  std::vector<float> f32(Image::n_f32(segcap) * stride); std::vector<int32_t> i32(Image::n_i32(segcap) * stride); std::vector<double> f64(Image::n_f64(segcap) * stride);
   Image img{f32.data(), i32.data(), f64.data(), stride, segcap};
   for (int64_t c = 0; c < n; ++c) { blockIdx.x = (unsigned)c; help_setup_kernel(B, img, nullptr, flags, topo, nullptr); }
   SimArgs A; A.img = img; A.pre = pre.data(); A.tmp = tmp.data(); A.rad = rad.data(); A.years = b->years; A.n_years = ny; A.n_cells = n; A.perm = nullptr;
@@ -37,3 +37,7 @@ extern "C" int emu_run(const help_b200_batch* b, float* monthly, float* yearly, 
   for (int64_t c = 0; c < n; ++c) { blockIdx.x = (unsigned)c; help_sim_kernel<67>(A); }
   return 0;
 }
+#ifdef HELP_EMU_COUNT
+extern "C" void emu_cap_counts(long long* out) { for (int i = 0; i < 8; ++i) out[i] = g_cap[i]; }
+extern "C" void emu_pow_counts(long long* out) { for (int i = 0; i < 4096; ++i) { out[i] = g_pow_count[i]; g_pow_count[i] = 0; } }
+#endif
