@@ -300,6 +300,9 @@ __device__ __noinline__ void route_subprofile(const Image& img, int64_t s, const
       for (; J + 1 < NSEGL; J += 2) {
         const CapIn a = cap_load(img, s, J, DT), b = cap_load(img, s, J + 1, DT);
         const float ra = cap_relsw(a, SW[J + 1] + (BAL[J + 1] / 2.0)), rb = cap_relsw(b, SW[J + 2] + (BAL[J + 2] / 2.0));
+#ifdef HELP_DBG_PRE2
+        HELP_DBG_PRE2
+#endif
         double pa, pb;
         r8_pow2((double)ra, a.nil1, (double)rb, b.nil1, pa, pb);
         r8_pow2(cap_ratio(a, pa), a.lam, cap_ratio(b, pb), b.lam, pa, pb);
@@ -341,6 +344,9 @@ __device__ __noinline__ void route_subprofile(const Image& img, int64_t s, const
       else if (kind == 2) { swl = fc; LOW = __ldg(&img.SD(SD_LOWFC, J, s)); }
       else { swl = ul; LOW = kdt; }            // ((ul - rs)/(ul - rs))**C == 1
       const double base = SW[J] + (BAL[J] / 2.0);                     // storage at the start of the step
+#ifdef HELP_DBG_SWEEP
+      HELP_DBG_SWEEP
+#endif
       double DRNMAX = base + drin + DSUBj - Ej - swl;
       if (J == NSEGL) {
         if (bottom) {

@@ -66,3 +66,11 @@ static long long g_cap[8]; static float g_prev_relsw[128];
 #define r8_pow(x, y) (g_pow_count[__LINE__ & 4095]++, helpmath::det_pow(x, y))
 #define r8_pow2(x0, y0, x1, y1, r0, r1) (g_pow_count[__LINE__ & 4095] += 2, helpmath::det_pow2(x0, y0, x1, y1, r0, r1))
 #endif
+
+#ifdef HELP_EMU_MEMO   // per-cell event streams: would a memo of the previous evaluation have hit?
+#include <vector>
+struct MemoStat { std::vector<unsigned char> pre, swp; float prelsw[128]; double pb[128], pd[128], pe[128], ps[128]; };
+static MemoStat g_memo[4096];
+#define HELP_DBG_PRE2 { MemoStat& M = g_memo[s]; M.pre.push_back(ra == M.prelsw[J]); M.pre.push_back(rb == M.prelsw[J + 1]); M.prelsw[J] = ra; M.prelsw[J + 1] = rb; }
+#define HELP_DBG_SWEEP { MemoStat& M = g_memo[s]; bool hit = (base == M.pb[J] && drin == M.pd[J] && Ej == M.pe[J] && swl == M.ps[J]); M.swp.push_back(hit); M.pb[J] = base; M.pd[J] = drin; M.pe[J] = Ej; M.ps[J] = swl; }
+#endif

@@ -41,3 +41,7 @@ extern "C" int emu_run(const help_b200_batch* b, float* monthly, float* yearly, 
 extern "C" void emu_cap_counts(long long* out) { for (int i = 0; i < 8; ++i) out[i] = g_cap[i]; }
 extern "C" void emu_pow_counts(long long* out) { for (int i = 0; i < 4096; ++i) { out[i] = g_pow_count[i]; g_pow_count[i] = 0; } }
 #endif
+#ifdef HELP_EMU_MEMO
+extern "C" long long emu_memo_len(int cell, int which) { return which ? g_memo[cell].swp.size() : g_memo[cell].pre.size(); }
+extern "C" void emu_memo_get(int cell, int which, unsigned char* out) { auto& v = which ? g_memo[cell].swp : g_memo[cell].pre; for (size_t i = 0; i < v.size(); ++i) out[i] = v[i]; }
+#endif

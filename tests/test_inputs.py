@@ -1,0 +1,71 @@
+"""Host packers: Fortran formatted-read semantics and the reference's text quantisation.
+
+The reference hands the engine TEXT (D4/D7/D13 files, D10/D11 records).  Two
+packers must produce the same numbers: `inputs.batch_from_cellparams` (parses that text like
+HELP3O.FOR's formatted READs) and `grid.batch_from_grid` (quantises arrays like the
+formatters, no text)."""
+import numpy as np
+import pytest
+
+from pyhelp_b200 import grid as G
+from pyhelp_b200 import inputs, synth
+from pyhelp_b200 import _native as N
+
+
+@pytest.mark.parametrize("family", ["natural3", "mixed", "landfill"])
+def test_vectorised_packer_equals_text_round_trip(tmp_path, family):
+    maker = {"natural3": synth.grid_natural_3layer, "mixed": synth.grid_mixed, "landfill": synth.grid_landfill}[family]
+    res = maker(50, seed=13)
+    g, ex = res if isinstance(res, tuple) else (res, None)
+    ny, nn = 2, 5
+    wx = synth.synth_weather(nn, 2003, ny, seed=2)
+    files = synth.write_weather_files(str(tmp_path), wx)
+    node = synth.assign_nodes(50, nn)
+    cp = synth.cellparams_from_grid(g, files, node, node, node, ny, tfsoil_c=-3.0, sf_edepth=0.15, sf_cn=1.15, ex=ex)
+    a = inputs.batch_from_cellparams(cp)
+    b = G.batch_from_grid(g, wx["years_of_day"], wx["precip"], wx["airtemp"], wx["solrad"], node, node, node,
+                          tfsoil_c=-3.0, sf_edepth=0.15, sf_cn=1.15, extra_layers=ex)
+    assert (a.n_cells, a.n_years, a.max_layers) == (b.n_cells, b.n_years, b.max_layers)
+    for k in ("years", "pre", "tmp", "rad", "iu4", "iu7", "iu13", "tm_normals", "idfs", "cell_f32", "cell_i32",
+              "layer_f32", "layer_i32", "layer_rc"):
+        assert np.array_equal(getattr(a, k), getattr(b, k)), k
+    assert a.names == b.names
+
+
+def test_fortran_read_semantics():
+    rec = inputs._records(["  12 3.5    7", "", " 1.5      25"], 80)
+    recd = inputs._records(["1.5D2"], 80)
+    # Fw.d: implied decimals only without an explicit point; blank field = 0
+    assert inputs._to_real(inputs._field(rec, 0, 4), 1, np.float32)[:3].tolist() == [np.float32(1.2), 0.0, np.float32(1.5)]
+    assert inputs._to_real(inputs._field(rec, 4, 4), 2, np.float32)[0] == np.float32(3.5)
+    assert inputs._to_int(inputs._field(rec, 8, 5))[:3].tolist() == [7, 0, 25]
+    assert inputs._to_real(inputs._field(recd, 0, 5), 0, np.float64)[0] == 150.0      # D exponent
+
+
+def test_quantisation_matches_python_format():
+    x = np.array([0.125, 0.375, 2.5, 1e-15, 123.4567, 0.0005, 0.0015])
+    for d in (0, 1, 2, 3, 14):
+        want = np.array([float(("{0:.%df}" % d).format(v)) for v in x])
+        assert np.array_equal(G.quantize(x, d), want), d
+
+
+def test_rcra_records_parse(rcra_dir):
+    import os.path as osp
+    d10 = np.char.ljust(open(osp.join(rcra_dir, "RCRA.D10")).read().splitlines(), 80).astype("S80")
+    d11 = np.char.ljust(open(osp.join(rcra_dir, "RCRA.D11")).read().splitlines(), 80).astype("S80")
+    cp = {"rcra": (osp.join(rcra_dir, "RCRA.D4"), osp.join(rcra_dir, "RCRA.D7"), osp.join(rcra_dir, "RCRA.D13"),
+                   d11.reshape(-1, 1), d10, "x", 0, 1, 0, 0, 3, 32.0)}            # (n,1) and (n,) shapes both accepted
+    b = inputs.batch_from_cellparams(cp)
+    assert b.n_cells == 1 and b.n_years == 3 and b.max_layers == 11
+    assert b.layer_i32[N.HL_TYPE, :, 0].tolist() == [1, 2, 4, 3, 1, 2, 2, 4, 2, 4, 3]      # RCRA.OUT layer list
+    assert b.cell_i32[N.HB_IU10, 0] == 1 and b.cell_i32[N.HB_IU11, 0] == 1                # IP units
+    assert b.idfs[0, 0] == 8
+    assert b.tm_normals[0].max() > 60                                                     # monthly normals present (deg F)
+
+
+def test_errors():
+    with pytest.raises(ValueError):
+        inputs.batch_from_cellparams({})
+    d = np.char.ljust(np.array(["a", "b", "c"]), 80).astype("S80")
+    with pytest.raises(FileNotFoundError):
+        inputs.batch_from_cellparams({"x": ("/nonexistent.D4", "/n.D7", "/n.D13", d, d, "o", 0, 1, 0, 0, 1, 32.0)})

@@ -1,0 +1,84 @@
+"""Host-side logic of the multi-GPU path, on CPU: shard arithmetic, weather-node compaction,
+and the gather of yearly summaries with world_size 2 over gloo."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from pyhelp_b200 import grid as G
+from pyhelp_b200 import sharding, synth
+from pyhelp_b200 import _native as N
+
+
+def test_shard_ranges_cover_everything():
+    for n in (0, 1, 7, 100, 100_001):
+        for w in (1, 2, 3, 8):
+            rs = [sharding.shard_range(n, w, r) for r in range(w)]
+            assert rs[0][0] == 0 and rs[-1][1] == n
+            assert all(rs[i][1] == rs[i + 1][0] for i in range(w - 1))
+            sizes = [b - a for a, b in rs]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def make_batch(n=40, nn=8, ny=1):
+    g = synth.grid_natural_3layer(n, seed=3)
+    wx = synth.synth_weather(nn, 2001, ny, seed=4)
+    node = synth.assign_nodes(n, nn)
+    return G.batch_from_grid(g, wx["years_of_day"], wx["precip"], wx["airtemp"], wx["solrad"], node, node, node)
+
+
+def test_shard_batch_compacts_weather_nodes():
+    b = make_batch()
+    parts = [sharding.shard_batch(b, 4, r) for r in range(4)]
+    assert sum(p.n_cells for p in parts) == b.n_cells
+    for r, p in enumerate(parts):
+        a, e = sharding.shard_range(b.n_cells, 4, r)
+        assert p.pre.shape[0] == 2 and p.tmp.shape[0] == 2 and p.rad.shape[0] == 2      # 8 nodes / 4 ranks
+        # every cell still points at ITS weather rows
+        for i in range(p.n_cells):
+            assert np.array_equal(p.pre[p.cell_i32[N.HB_NODE_P, i]], b.pre[b.cell_i32[N.HB_NODE_P, a + i]])
+            assert np.array_equal(p.rad[p.cell_i32[N.HB_NODE_R, i]], b.rad[b.cell_i32[N.HB_NODE_R, a + i]])
+            assert np.array_equal(p.idfs[p.cell_i32[N.HB_NODE_R, i]], b.idfs[b.cell_i32[N.HB_NODE_R, a + i]])
+        assert np.array_equal(p.cell_f32, b.cell_f32[:, a:e]) and p.names == b.names[a:e]
+        p.as_struct()          # all arrays contiguous
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _worker(rank, world, port, n_total, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    a, b = sharding.shard_range(n_total, world, rank)
+    # a recognisable payload: value = global cell index + 1000*row + 10*year
+    idx = torch.arange(a, b, dtype=torch.float32)
+    y = idx[None, None, :] + 1000.0 * torch.arange(5)[:, None, None] + 10.0 * torch.arange(3)[None, :, None]
+    out = sharding.gather_yearly(y, n_total, world, rank)
+    if rank == 0:
+        q.put(out.numpy())
+    else:
+        assert out is None
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_total", [11, 64])
+def test_gather_yearly_gloo_world2(n_total):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, n_total, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    want = (np.arange(n_total, dtype=np.float32)[None, None, :] + 1000.0 * np.arange(5)[:, None, None]
+            + 10.0 * np.arange(3)[None, :, None])
+    assert got.shape == (5, 3, n_total) and np.array_equal(got, want)
