@@ -107,12 +107,26 @@ enum ImgPI : int {
 };
 // i32 per segment: bit0 = LAYSEG(J,2) < LD(NPROF) (F:4494), bit1 = the same for J+1 (F:4499)
 
+// ---- packed per-segment records: what the routing loop reads every sub-step ---------------------
+// The SoA fields above cost one 4-byte load and one address computation each; the routing
+// loop reads ~15 of them per segment per sub-step for every resident cell, far more than
+// L1 holds.  The hot ones are therefore also stored as 16-byte vectors, [segment][vector][cell]:
+// one coalesced 512-byte line per warp and vector.
+//   float4 R0 = {UL, FC, WP, RS}    R1 = {LAMBDA, BUB, RC, THICK}   R2 = {SUBIN, RELMIN, flags, -}
+//   double2 Q0 = {C, -1/LAMBDA}     Q1 = {B (Newton), LOW at WP}    Q2 = {LOW at FC, -}
+constexpr int kRecF = 3, kRecD = 3;
+
 struct Image {
   float* f32;
   int32_t* i32;
   double* f64;
   int64_t stride;   // cells per field row
   int segcap;
+  float4* rec4;     // [segcap][kRecF][stride]
+  double2* recd;    // [segcap][kRecD][stride]
+
+  __device__ __forceinline__ float4& R4(int v, int j, int64_t c) const { return rec4[((int64_t)(j - 1) * kRecF + v) * stride + c]; }
+  __device__ __forceinline__ double2& RD(int v, int j, int64_t c) const { return recd[((int64_t)(j - 1) * kRecD + v) * stride + c]; }
 
   __host__ __device__ static int64_t n_f32(int segcap) { return F_NSCALAR + P_NF * kNProf + (int64_t)S_NF * segcap; }
   __host__ __device__ static int64_t n_i32(int segcap) { return I_NSCALAR + Q_NF * kNProf + segcap; }

@@ -676,6 +676,15 @@ help_setup_kernel(BatchDev B, Image img, const int32_t* __restrict__ perm, uint3
       img.SD(SD_LOWWP, J, slot) = lowwp; img.SD(SD_LOWFC, J, slot) = lowfc;
     }
     for (int J = 1; J < img.segcap; ++J) img.SI(J, slot) = (img.SI(J, slot) & 1) | ((img.SI(J + 1, slot) & 1) << 1);
+    // packed copies for the routing loop (help_image.h "packed per-segment records")
+    for (int J = 1; J <= img.segcap; ++J) {
+      img.R4(0, J, slot) = make_float4(img.SF(S_UL, J, slot), img.SF(S_FC, J, slot), img.SF(S_WP, J, slot), img.SF(S_RS, J, slot));
+      img.R4(1, J, slot) = make_float4(img.SF(S_LAM, J, slot), img.SF(S_BUB, J, slot), img.SF(S_RC, J, slot), img.SF(S_THICK, J, slot));
+      img.R4(2, J, slot) = make_float4(img.SF(S_SUBIN, J, slot), img.SF(S_RELMIN, J, slot), __int_as_float(img.SI(J, slot)), 0.f);
+      img.RD(0, J, slot) = make_double2(img.SD(SD_C, J, slot), img.SD(SD_NIL, J, slot));
+      img.RD(1, J, slot) = make_double2(img.SD(SD_BC, J, slot), img.SD(SD_LOWWP, J, slot));
+      img.RD(2, J, slot) = make_double2(img.SD(SD_LOWFC, J, slot), 0.0);
+    }
   }
   const int hemi = (C.ULAT >= 0.0f) ? 0 : 1;
   const int IDFS = B.idfs[(int64_t)node_r * 2 + hemi];

@@ -509,11 +509,18 @@ struct Surf {      // REAL*4 surface-process state of one cell
   float RAIN, SMELT, GMRO, ADDRUN, RUN, PINF, ETT, ESS, EP, ES, ETO, ABST, ET[8];
 };
 
+// Block shape.  Every warp of a block is kept in the same day of the simulation by one
+// barrier per day (HELP_SIM_DAYSYNC): the routing code is several times larger than the
+// 32 KB L1.5 instruction cache, and warps that run the same region together share its fetches
+// (measured on B200: +15 % throughput, profiles/r1_notes.md).
 #ifndef HELP_SIM_THREADS
-#define HELP_SIM_THREADS 64
+#define HELP_SIM_THREADS 128
 #endif
 #ifndef HELP_SIM_MINBLOCKS
-#define HELP_SIM_MINBLOCKS 12
+#define HELP_SIM_MINBLOCKS 6
+#endif
+#ifndef HELP_SIM_NO_DAYSYNC
+#define HELP_SIM_DAYSYNC 1
 #endif
 template <int MAXSEG>
 __global__ void __launch_bounds__(HELP_SIM_THREADS, HELP_SIM_MINBLOCKS) help_sim_kernel(SimArgs A) {
@@ -584,7 +591,18 @@ __global__ void __launch_bounds__(HELP_SIM_THREADS, HELP_SIM_MINBLOCKS) help_sim
     }
   }
   // ---- state (run_simulation F:200-317; READIN F:1344-1351; INITIA F:2437-2442) ---------------
+  // segment state in shared memory: the per-thread working set of all resident cells is far
+  // larger than L1, so thread-local arrays were evicted to L2/HBM between sub-steps.  One row
+  // per thread, odd row length (in doubles) = conflict-free 64-bit accesses.
+#ifdef HELP_SIM_STATE_SMEM
+  extern __shared__ double state_smem[];
+  constexpr int SSTR = (MAXSEG + 2) | 1;
+  double* SW = state_smem + (int)threadIdx.x * SSTR;
+  double* BAL = state_smem + ((int)blockDim.x + (int)threadIdx.x) * SSTR;
+  double DRIN[MAXSEG + 3], LOWc[MAXSEG + 2];
+#else
   double SW[MAXSEG + 2], BAL[MAXSEG + 2], DRIN[MAXSEG + 3], LOWc[MAXSEG + 2];
+#endif
   float SWLc[MAXSEG + 2];
   for (int J = 1; J <= NSEG; ++J) { SW[J] = (double)img.SF(S_SW0, J, s); BAL[J] = 0.0; }
   SW[0] = BAL[0] = 0.0; SW[NSEG + 1] = BAL[NSEG + 1] = 0.0;
@@ -651,6 +669,9 @@ __global__ void __launch_bounds__(HELP_SIM_THREADS, HELP_SIM_MINBLOCKS) help_sim
       const float* __restrict__ ytmp = wtmp + (int64_t)iy * kDays;
       const float* __restrict__ yrad = wrad + (int64_t)iy * kDays;
       for (int IDA = 1; IDA <= ND; ++IDA) {               // DO 1100
+#ifdef HELP_SIM_DAYSYNC
+        __syncthreads();      // keep the block's warps in the same code region (instruction cache)
+#endif
         const float PRE = __ldg(ypre + IDA - 1), TMPF = __ldg(ytmp + IDA - 1), RAD = __ldg(yrad + IDA - 1);
         const float RH = RHq[(IDA <= 91) ? 0 : (IDA <= 182) ? 1 : (IDA <= 274) ? 2 : 3];
         PREM = PREM + PRE;

@@ -18,6 +18,13 @@ struct dim3s { unsigned x, y, z; };
 static thread_local dim3s blockIdx{0, 0, 0}, threadIdx{0, 0, 0}, blockDim{1, 1, 1}, gridDim{1, 1, 1};
 template <typename T> static inline T __ldg(const T* p) { return *p; }
 static inline float __int_as_float(int i) { float f; std::memcpy(&f, &i, 4); return f; }
+static inline int __float_as_int(float f) { int i; std::memcpy(&i, &f, 4); return i; }
+struct float4 { float x, y, z, w; }; struct double2 { double x, y; };
+static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
+static inline double2 make_double2(double x, double y) { return double2{x, y}; }
+static inline unsigned __ballot_sync(unsigned, int p) { return p ? 1u : 0u; }
+static inline int __any_sync(unsigned, int p) { return p; }
+static inline unsigned __activemask() { return 1u; }
 static inline float __fmul_rn(float a, float b) { return a * b; }
 static inline float __fadd_rn(float a, float b) { return a + b; }
 #include <math.h>
