@@ -72,7 +72,7 @@ struct help_b200_engine {
   int32_t *d_cell_i32 = nullptr, *d_layer_i32 = nullptr;
   double* d_layer_rc = nullptr;
   float* d_img_f32 = nullptr; int32_t* d_img_i32 = nullptr; double* d_img_f64 = nullptr;
-  float4* d_img_rec4 = nullptr; double2* d_img_recd = nullptr;
+  char* d_img_rec = nullptr;
   float *d_monthly = nullptr, *d_yearly = nullptr, *d_raw = nullptr;
   uint32_t* d_flags = nullptr; int32_t* d_topo = nullptr;
   uint64_t *d_key = nullptr, *d_key2 = nullptr; int32_t *d_perm = nullptr, *d_iota = nullptr;
@@ -89,7 +89,7 @@ static void engine_free(help_b200_engine* e) {
   cudaSetDevice(e->device);
   void* ptrs[] = {e->d_years, e->d_pre, e->d_tmp, e->d_rad, e->d_tm, e->d_iu4, e->d_iu7, e->d_iu13, e->d_idfs,
                   e->d_cell_f32, e->d_layer_f32, e->d_cell_i32, e->d_layer_i32, e->d_layer_rc, e->d_img_f32,
-                  e->d_img_i32, e->d_img_f64, e->d_img_rec4, e->d_img_recd, e->d_monthly, e->d_yearly, e->d_raw, e->d_flags, e->d_topo,
+                  e->d_img_i32, e->d_img_f64, e->d_img_rec, e->d_monthly, e->d_yearly, e->d_raw, e->d_flags, e->d_topo,
                   e->d_key, e->d_key2, e->d_perm, e->d_iota, e->d_cub};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (auto& ev : e->ev) if (ev) cudaEventDestroy(ev);
@@ -190,8 +190,7 @@ extern "C" int help_b200_engine_create(const help_b200_batch* b, int want_monthl
   TRY(dev_alloc(&e->d_img_f32, (size_t)Image::n_f32(e->segcap) * e->stride));
   TRY(dev_alloc(&e->d_img_i32, (size_t)Image::n_i32(e->segcap) * e->stride));
   TRY(dev_alloc(&e->d_img_f64, (size_t)Image::n_f64(e->segcap) * e->stride));
-  TRY(dev_alloc(&e->d_img_rec4, (size_t)e->segcap * kRecF * e->stride));
-  TRY(dev_alloc(&e->d_img_recd, (size_t)e->segcap * kRecD * e->stride));
+  TRY(dev_alloc(&e->d_img_rec, (size_t)Image::rec_bytes(e->stride, e->segcap)));
   if (e->want_monthly) TRY(dev_alloc(&e->d_monthly, (size_t)HR_NROWS * ny * 12 * n));
   if (e->want_raw) TRY(dev_alloc(&e->d_raw, (size_t)HELP_B200_RAW_ROWS * ny * 12 * n));
   TRY(dev_alloc(&e->d_yearly, (size_t)HY_NROWS * ny * n));
@@ -249,7 +248,11 @@ template <int MAXSEG>
 static void launch_sim(const SimArgs& A, int64_t n, cudaStream_t st) {
   const int th = HELP_SIM_THREADS;
 #ifdef HELP_SIM_STATE_SMEM
-  const size_t smem = (size_t)2 * th * ((MAXSEG + 2) | 1) * sizeof(double);
+#ifdef HELP_SIM_DRIN_SMEM
+  const size_t smem = (size_t)th * (2 * (MAXSEG + 2) + MAXSEG + 3) * sizeof(double);
+#else
+  const size_t smem = (size_t)2 * th * (MAXSEG + 2) * sizeof(double);
+#endif
   cudaFuncSetAttribute(help_sim_kernel<MAXSEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 #else
   const size_t smem = 0;
@@ -263,7 +266,7 @@ extern "C" int help_b200_engine_simulate(help_b200_engine* e, void* stream) {
   cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
   const int64_t n = e->n;
   e->n_launches = 0;
-  Image img{e->d_img_f32, e->d_img_i32, e->d_img_f64, e->stride, e->segcap, e->d_img_rec4, e->d_img_recd};
+  Image img{e->d_img_f32, e->d_img_i32, e->d_img_f64, e->stride, e->segcap, e->d_img_rec};
   CU(cudaEventRecord(e->ev[0], st));
   if (n > 0) {
     const unsigned gs = (unsigned)((n + 63) / 64);

@@ -103,18 +103,32 @@ enum ImgPI : int {
   Q_LPQ,         // LPQ(n)
   Q_LTYPE,       // LAYER(LP(n)) (F:5292)
   Q_LD,          // LD(n)
+  Q_SUBIN,       // 1 if any segment of the subprofile has subsurface inflow (SUBINS > 0)
   Q_NF
 };
 // i32 per segment: bit0 = LAYSEG(J,2) < LD(NPROF) (F:4494), bit1 = the same for J+1 (F:4499)
 
-// ---- packed per-segment records: what the routing loop reads every sub-step ---------------------
-// The SoA fields above cost one 4-byte load and one address computation each; the routing
-// loop reads ~15 of them per segment per sub-step for every resident cell, far more than
-// L1 holds.  The hot ones are therefore also stored as 16-byte vectors, [segment][vector][cell]:
-// one coalesced 512-byte line per warp and vector.
-//   float4 R0 = {UL, FC, WP, RS}    R1 = {LAMBDA, BUB, RC, THICK}   R2 = {SUBIN, RELMIN, flags, -}
-//   double2 Q0 = {C, -1/LAMBDA}     Q1 = {B (Newton), LOW at WP}    Q2 = {LOW at FC, -}
-constexpr int kRecF = 3, kRecD = 3;
+// ---- routing records: what the sub-daily routing loop reads every sub-step ---------------------
+// The routing loop (help_sim.cuh route_subprofile) touches ~14 constants of every segment of
+// every resident cell 4..288 times per simulated day; this stream, not the weather or the
+// results, is the kernel's memory traffic.  Its layout is therefore tile-major and vectorised:
+//     rec[tile = cell/32][segment][vector][lane = cell%32]      (16 bytes per lane and vector)
+// so that (1) a warp reads one contiguous 512-byte row per vector, (2) every vector of a segment
+// sits at a compile-time offset from ONE per-thread pointer that advances by kRecBytes per
+// segment, and (3) all loads of a segment can be issued together, one segment ahead of their use.
+// REAL*4 members hold the reference's REAL*4 values; the REAL*8 members hold values the reference
+// recomputes from them every sub-step (same operations, same order; F:4329-4466), which depend
+// only on the segment and on DT = 1/NSTEP(n).
+//   RV_A float4  {UL, RSUL, WPUL, FCUL}                       inches of water
+//   RV_B float4  {XLAMBU, BUBUL, RELMIN, flags}               RELMIN = REAL*4 (WPUL-RSUL)/(UL-RSUL), F:4329;
+//                                                             flags: bit0 = above the drain layer, bit1 = so is J+1 (F:4494,4499)
+//   RV_C double2 {1/(UL-RS) correctly rounded, K dt}          (fdiv_by below)
+//   RV_D double2 {C = 3 + 2/lambda, -1/lambda}                (F:4420, 4465; F:4334, 4360)
+//   RV_E double2 {B = K dt (1/(UL-RS))**C, LOW at SWLIM = WP} (F:4466; F:4420)
+//   RV_F double2 {LOW at SWLIM = FC, (STHICK, SUBINS) as two REAL*4}
+enum RecV : int { RV_A = 0, RV_B, RV_C, RV_D, RV_E, RV_F, kRecV };
+constexpr int kRecBytes = kRecV * 512;
+struct alignas(16) RecTail { double lowfc; float thick, subin; };   // RV_F
 
 struct Image {
   float* f32;
@@ -122,11 +136,13 @@ struct Image {
   double* f64;
   int64_t stride;   // cells per field row
   int segcap;
-  float4* rec4;     // [segcap][kRecF][stride]
-  double2* recd;    // [segcap][kRecD][stride]
+  char* rec;        // routing records, [stride/32][segcap][kRecBytes]
 
-  __device__ __forceinline__ float4& R4(int v, int j, int64_t c) const { return rec4[((int64_t)(j - 1) * kRecF + v) * stride + c]; }
-  __device__ __forceinline__ double2& RD(int v, int j, int64_t c) const { return recd[((int64_t)(j - 1) * kRecD + v) * stride + c]; }
+  // per-thread base pointer of cell c's records (vector RV_A of segment 1)
+  __host__ __device__ __forceinline__ char* rec_p(int64_t c) const {
+    return rec + (c >> 5) * ((int64_t)segcap * kRecBytes) + (c & 31) * 16;
+  }
+  __host__ __device__ static int64_t rec_bytes(int64_t stride, int segcap) { return (stride / 32) * (int64_t)segcap * kRecBytes; }
 
   __host__ __device__ static int64_t n_f32(int segcap) { return F_NSCALAR + P_NF * kNProf + (int64_t)S_NF * segcap; }
   __host__ __device__ static int64_t n_i32(int segcap) { return I_NSCALAR + Q_NF * kNProf + segcap; }
@@ -154,6 +170,16 @@ struct Image {
   }
 };
 
+// vector accessors: p = rec_p(c) advanced to the segment ((J-1) * kRecBytes)
+#if defined(__CUDA_ARCH__)
+template <int V> __device__ __forceinline__ float4 rec_f4(const char* p) { return __ldg((const float4*)(p + V * 512)); }
+template <int V> __device__ __forceinline__ double2 rec_d2(const char* p) { return __ldg((const double2*)(p + V * 512)); }
+#else
+template <int V> inline float4 rec_f4(const char* p) { return *(const float4*)(p + V * 512); }
+template <int V> inline double2 rec_d2(const char* p) { return *(const double2*)(p + V * 512); }
+#endif
+__host__ __device__ __forceinline__ RecTail rec_tail(const char* p) { return *(const RecTail*)(p + RV_F * 512); }
+
 // cell status bits (mirrors include/help_b200.h)
 constexpr uint32_t kFlagNonConv = 0x1u, kFlagNaN = 0x2u, kFlagOverflow = 0x4u, kFlagRecirc = 0x8u,
                    kFlagBadCell = 0x10u;
@@ -173,11 +199,37 @@ __host__ __device__ __forceinline__ double r8_pow(double x, double y) { return h
 __host__ __device__ __forceinline__ void r8_pow2(double x0, double y0, double x1, double y1, double& r0, double& r1) {
   helpmath::det_pow2(x0, y0, x1, y1, r0, r1);   // two independent powers, same bits as r8_pow
 }
+__host__ __device__ __forceinline__ void r8_pow_sb(double x, double y0, double y1, double& r0, double& r1) {
+  helpmath::det_pow_samebase(x, y0, y1, r0, r1);   // x**y0 and x**y1, same bits as two r8_pow calls
+}
 __host__ __device__ __forceinline__ double r8_log(double x) { return helpmath::det_log(x); }
 __host__ __device__ __forceinline__ double r8_atan(double x) { return helpmath::det_atan(x); }
 __host__ __device__ __forceinline__ double r8_sin(double x) { return helpmath::det_sin(x); }
 __host__ __device__ __forceinline__ double r8_cos(double x) { return helpmath::det_cos(x); }
 __host__ __device__ __forceinline__ double r8_sqrt(double x) { return helpmath::hm_sqrt(x); }
 #endif
+
+
+// a / b, correctly rounded, given rb = RN(1/b) (a constant of the segment).  q0 = RN(a rb) is
+// within 2 ulp of a/b; one residual correction makes it faithful, and a second one gives
+// RN(a/b) exactly (Markstein's theorem: y = RN(1/b), q faithful, r = a - b q exact
+// => RN(q + r y) = RN(a/b)).  Same bits as the IEEE division the reference executes, at 5
+// FP64 operations instead of the ~15 + slow-path test of div.rn.f64.  Domain: b, 1/b, a/b
+// finite and normal (or a = 0); tests/test_help_math.py checks it against '/'.
+__host__ __device__ __forceinline__ double fdiv_by(double a, double b, double rb) {
+#if defined(__CUDA_ARCH__)
+  double q = __dmul_rn(a, rb);
+  double r = __fma_rn(-q, b, a);
+  q = __fma_rn(r, rb, q);
+  r = __fma_rn(-q, b, a);
+  return __fma_rn(r, rb, q);
+#else
+  double q = a * rb;
+  double r = __builtin_fma(-q, b, a);
+  q = __builtin_fma(r, rb, q);
+  r = __builtin_fma(-q, b, a);
+  return __builtin_fma(r, rb, q);
+#endif
+}
 
 }  // namespace helpb200

@@ -676,14 +676,32 @@ help_setup_kernel(BatchDev B, Image img, const int32_t* __restrict__ perm, uint3
       img.SD(SD_LOWWP, J, slot) = lowwp; img.SD(SD_LOWFC, J, slot) = lowfc;
     }
     for (int J = 1; J < img.segcap; ++J) img.SI(J, slot) = (img.SI(J, slot) & 1) | ((img.SI(J + 1, slot) & 1) << 1);
-    // packed copies for the routing loop (help_image.h "packed per-segment records")
-    for (int J = 1; J <= img.segcap; ++J) {
-      img.R4(0, J, slot) = make_float4(img.SF(S_UL, J, slot), img.SF(S_FC, J, slot), img.SF(S_WP, J, slot), img.SF(S_RS, J, slot));
-      img.R4(1, J, slot) = make_float4(img.SF(S_LAM, J, slot), img.SF(S_BUB, J, slot), img.SF(S_RC, J, slot), img.SF(S_THICK, J, slot));
-      img.R4(2, J, slot) = make_float4(img.SF(S_SUBIN, J, slot), img.SF(S_RELMIN, J, slot), __int_as_float(img.SI(J, slot)), 0.f);
-      img.RD(0, J, slot) = make_double2(img.SD(SD_C, J, slot), img.SD(SD_NIL, J, slot));
-      img.RD(1, J, slot) = make_double2(img.SD(SD_BC, J, slot), img.SD(SD_LOWWP, J, slot));
-      img.RD(2, J, slot) = make_double2(img.SD(SD_LOWFC, J, slot), 0.0);
+  }
+  // ---- routing records (help_image.h RecF / RecD) ---------------------------------------------------
+  {
+    char* p = img.rec_p(slot);
+    for (int J = 1; J <= img.segcap; ++J, p += kRecBytes) {
+      const bool in = (J <= S.NSEG);
+      const float ul = img.SF(S_UL, J, slot), rs = img.SF(S_RS, J, slot);
+      const double span = (double)ul - (double)rs;
+      int N = 1, eseg = S.NSEGn[1];
+      while (N < 6 && J > eseg) { ++N; eseg += S.NSEGn[N]; }
+      const double DT = 1.0 / (double)T.NSTEP[N];
+      *(float4*)(p + RV_A * 512) = make_float4(ul, rs, img.SF(S_WP, J, slot), img.SF(S_FC, J, slot));
+      *(float4*)(p + RV_B * 512) = make_float4(img.SF(S_LAM, J, slot), img.SF(S_BUB, J, slot), img.SF(S_RELMIN, J, slot),
+                                               __int_as_float(img.SI(J, slot)));
+      *(double2*)(p + RV_C * 512) = make_double2(in ? 1.0 / span : 0.0, in ? (double)img.SF(S_RC, J, slot) * DT : 0.0);
+      *(double2*)(p + RV_D * 512) = make_double2(img.SD(SD_C, J, slot), img.SD(SD_NIL, J, slot));
+      *(double2*)(p + RV_E * 512) = make_double2(img.SD(SD_BC, J, slot), img.SD(SD_LOWWP, J, slot));
+      RecTail t; t.lowfc = img.SD(SD_LOWFC, J, slot); t.thick = img.SF(S_THICK, J, slot); t.subin = img.SF(S_SUBIN, J, slot);
+      *(RecTail*)(p + RV_F * 512) = t;
+    }
+    int e2 = 0;
+    for (int N = 1; N <= 6; ++N) {
+      int any = 0;
+      for (int J = e2 + 1; J <= e2 + S.NSEGn[N]; ++J) if (img.SF(S_SUBIN, J, slot) != 0.0f) any = 1;
+      img.PI(Q_SUBIN, N, slot) = any;
+      e2 += S.NSEGn[N];
     }
   }
   const int hemi = (C.ULAT >= 0.0f) ? 0 : 1;

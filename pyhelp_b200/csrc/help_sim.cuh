@@ -205,59 +205,32 @@ __device__ __noinline__ double lateral_rate(const Image& img, int64_t s, int NSE
 // ---- one subprofile, one day (DRAIN/AVROUT/PROFIL/HEAD, F:4133-4617) ------------------
 // SW/BAL: per-segment state (1-based).  DRIN: scratch, DRIN[j] = inflow into segment j.
 // ET7[1..7]: today's evapotranspiration demand per evaporative segment (inches).
-// SWLc/LOWc: scratch of the capillary pre-pass (below).
+// Per-segment constants come from the routing records (help_image.h): one pointer pair walks
+// down the profile, every constant is a load at a compile-time offset.
 struct ProfC {
-  int n, NSEGB, NSEGE, NSEG, nstep, ibar, lat;
+  int n, NSEGB, NSEGE, NSEG, nstep, ibar, lat, subin;
   float drculs, dthics, slope, xleng, sublin;
   FmlC fml;
 };
 
-// Lower storage limit of segment J when it is in capillary equilibrium with the segment
-// below (F:4330-4340 == F:4356-4366) and the unrestricted drainage LOW at that limit
-// (F:4420-4421).  Both depend only on the state of J+1 at the start of the sub-step, so every
-// segment's pair is independent of the top-down routing order: the pre-pass evaluates them
-// for all segments of all 32 cells of a warp in lockstep, TWO segments per iteration through
-// the dual-issue power r8_pow2 (three powers per segment: psi, relative storage, LOW).
-struct CapIn {
-  double rs1, ul1, bub1, nil1, bub, lam, span, rs, wp, fc, kdt, C;
-  float relmin1;
-};
-__device__ __forceinline__ CapIn cap_load(const Image& img, int64_t s, int J, double DT) {
-  CapIn c;
-  c.rs1 = (double)__ldg(&img.SF(S_RS, J + 1, s)); c.ul1 = (double)__ldg(&img.SF(S_UL, J + 1, s));
-  c.bub1 = (double)__ldg(&img.SF(S_BUB, J + 1, s)); c.relmin1 = __ldg(&img.SF(S_RELMIN, J + 1, s));
-  c.nil1 = __ldg(&img.SD(SD_NIL, J + 1, s));
-  c.bub = (double)__ldg(&img.SF(S_BUB, J, s)); c.lam = (double)__ldg(&img.SF(S_LAM, J, s));
-  const double ul = (double)__ldg(&img.SF(S_UL, J, s));
-  c.rs = (double)__ldg(&img.SF(S_RS, J, s)); c.span = ul - c.rs;
-  c.wp = (double)__ldg(&img.SF(S_WP, J, s)); c.fc = (double)__ldg(&img.SF(S_FC, J, s));
-  c.kdt = (double)__ldg(&img.SF(S_RC, J, s)) * DT; c.C = __ldg(&img.SD(SD_C, J, s));
-  return c;
-}
-__device__ __forceinline__ float cap_relsw(const CapIn& c, double base1) {
-  float RELSW = (float)((base1 - c.rs1) / (c.ul1 - c.rs1));
-  if (RELSW < c.relmin1) RELSW = c.relmin1;
-  return RELSW;
-}
-__device__ __forceinline__ double cap_ratio(const CapIn& c, double psi_pow) {     // BUB(J)/PSIJP1
-  float PSIJP1 = (float)(c.bub1 * psi_pow);
-  if ((double)PSIJP1 < c.bub) PSIJP1 = (float)c.bub;
-  return c.bub / (double)PSIJP1;
-}
-__device__ __forceinline__ float cap_swlim(const CapIn& c, double rel_pow) {
-  const float RELSWL = (float)rel_pow;
-  float SWLIM = (float)(((double)RELSWL * c.span) + c.rs);
-  if ((double)SWLIM < c.wp) SWLIM = (float)c.wp;
-  if ((double)SWLIM > c.fc) SWLIM = (float)c.fc;
-  return SWLIM;
-}
+#ifdef HELP_SIM_STATE_SMEM
+#define HELP_SST ((int)blockDim.x)   // element stride of SW/BAL: [segment][thread] in shared memory
+#else
+#define HELP_SST 1                   // thread-local arrays
+#endif
+#define SWa(j) SW[(j) * HELP_SST]
+#define BALa(j) BAL[(j) * HELP_SST]
+#ifdef HELP_SIM_DRIN_SMEM
+#define DRINa(j) DRIN[(j) * HELP_SST]
+#else
+#define DRINa(j) DRIN[(j)]
+#endif
 
 template <int MAXSEG>
 __device__ __noinline__ void route_subprofile(const Image& img, int64_t s, const ProfC& P, float FIN,
                                               const float* __restrict__ ET7, int IFREZ,
                                               double* __restrict__ SW, double* __restrict__ BAL,
-                                              double* __restrict__ DRIN, float* __restrict__ SWLc,
-                                              double* __restrict__ LOWc, double& DRNo, double& PRCo,
+                                              double* __restrict__ DRIN, double& DRNo, double& PRCo,
                                               float& EXTRA, uint32_t& flag) {
   const int NSEGB = P.NSEGB, NSEGE = P.NSEGE, NSEG = P.NSEG, IBAR = P.ibar, LAT = P.lat;
   const int NSEGL = (IBAR == 0 || IBAR == 3) ? NSEGE : NSEGE - 1;
@@ -266,10 +239,17 @@ __device__ __noinline__ void route_subprofile(const Image& img, int64_t s, const
   const double DSUBE = (double)P.sublin * DT;            // DSUB(NSEGE)
   const bool bottom = (NSEGE == NSEG);
   const bool liner = !(IBAR == 0 || IBAR == 3);
+  const bool has_sub = (P.subin != 0);
+  const char* const p0 = img.rec_p(s) + (int64_t)(NSEGB - 1) * kRecBytes;
+  const char* const pL = p0 + (int64_t)(NSEGL - NSEGB) * kRecBytes;
+  const double LOWFC_L = rec_tail(pL).lowfc;            // SWLIM = FC occurs at segment NSEGL only
+  double Ed[8];                                          // E(J) = ET(J) dt of the evaporative segments
+#pragma unroll
+  for (int J = 1; J <= 7; ++J) Ed[J] = (double)ET7[J] * DT;
   double EXCESS = 0.0, PRC = 0.0, DRN = 0.0;
   EXTRA = 0.0f;
   for (int K = 1; K <= P.nstep; ++K) {
-    DRIN[NSEGB] = F + EXCESS;
+    DRINa(NSEGB) = F + EXCESS;
     EXCESS = 0.0;
     double QPERCY = 0.0, QLATY = 0.0;
     if (liner) {
@@ -277,11 +257,11 @@ __device__ __noinline__ void route_subprofile(const Image& img, int64_t s, const
       double THY = 0.0;
       for (int Kk = NSEGL; Kk >= NSEGB; --Kk) {
         const double fc = (double)__ldg(&img.SF(S_FC, Kk, s));
-        const double cur = SW[Kk] + (BAL[Kk] / 2.0);
+        const double cur = SWa(Kk) + (BALa(Kk) / 2.0);
         if (cur <= fc) break;
         const double th = (double)__ldg(&img.SF(S_THICK, Kk, s)), ul = (double)__ldg(&img.SF(S_UL, Kk, s));
         double XHEAD = th * (cur - fc) / (ul - fc);
-        if (XHEAD > th) XHEAD = th + SW[Kk] + (BAL[Kk] / 2.0) - ul;
+        if (XHEAD > th) XHEAD = th + SWa(Kk) + (BALa(Kk) / 2.0) - ul;
         THY = THY + XHEAD;
         XHEAD = XHEAD - th;
         if ((XHEAD + 0.00005) < 0.0) break;
@@ -293,40 +273,32 @@ __device__ __noinline__ void route_subprofile(const Image& img, int64_t s, const
         if (LAT == 1) QLATY = lateral_rate(img, s, NSEGB, NSEGL, THY, P.slope, P.xleng);
       }
     }
-    // ---- capillary pre-pass: limits of all segments that can take the capillary branch -------
-    // (J < NSEGL; which of them USE the value is decided in the routing loop below)
-    {
-      int J = NSEGB;
-      for (; J + 1 < NSEGL; J += 2) {
-        const CapIn a = cap_load(img, s, J, DT), b = cap_load(img, s, J + 1, DT);
-        const float ra = cap_relsw(a, SW[J + 1] + (BAL[J + 1] / 2.0)), rb = cap_relsw(b, SW[J + 2] + (BAL[J + 2] / 2.0));
-#ifdef HELP_DBG_PRE2
-        HELP_DBG_PRE2
-#endif
-        double pa, pb;
-        r8_pow2((double)ra, a.nil1, (double)rb, b.nil1, pa, pb);
-        r8_pow2(cap_ratio(a, pa), a.lam, cap_ratio(b, pb), b.lam, pa, pb);
-        const float la = cap_swlim(a, pa), lb = cap_swlim(b, pb);
-        r8_pow2(((double)la - a.rs) / a.span, a.C, ((double)lb - b.rs) / b.span, b.C, pa, pb);
-        SWLc[J] = la; LOWc[J] = a.kdt * pa; SWLc[J + 1] = lb; LOWc[J + 1] = b.kdt * pb;
-      }
-      if (J < NSEGL) {
-        const CapIn a = cap_load(img, s, J, DT);
-        const float ra = cap_relsw(a, SW[J + 1] + (BAL[J + 1] / 2.0));
-        const float la = cap_swlim(a, r8_pow(cap_ratio(a, r8_pow((double)ra, a.nil1)), a.lam));
-        SWLc[J] = la; LOWc[J] = a.kdt * r8_pow(((double)la - a.rs) / a.span, a.C);
-      }
-    }
     // ---- AVROUT (F:4287-4527): top -> bottom ---------------------------------------------------
-    for (int J = NSEGB; J <= NSEGL; ++J) {
-      const double ul = (double)__ldg(&img.SF(S_UL, J, s)), rs = (double)__ldg(&img.SF(S_RS, J, s));
-      const double wp = (double)__ldg(&img.SF(S_WP, J, s)), fc = (double)__ldg(&img.SF(S_FC, J, s));
-      const double kdt = (double)__ldg(&img.SF(S_RC, J, s)) * DT;
-      const double Ej = (J <= 7) ? (double)ET7[J] * DT : 0.0;
-      const double DSUBj = (double)__ldg(&img.SF(S_SUBIN, J, s)) * DT;
-      const double drin = DRIN[J];
+    // The record vectors and the state of segment J+1 are loaded at the top of iteration J:
+    // the capillary limit of J needs them, and they are segment J's own in the next iteration.
+    const char* p = p0;
+    float4 A = rec_f4<RV_A>(p), B = rec_f4<RV_B>(p);
+    double2 Cv = rec_d2<RV_C>(p), Dv = rec_d2<RV_D>(p);
+    double swj = SWa(NSEGB), balj = BALa(NSEGB);
+    double drin = DRINa(NSEGB);
+    for (int J = NSEGB; J <= NSEGL; ++J, p += kRecBytes) {
+      float4 A1 = A, B1 = B;
+      double2 C1 = Cv, D1 = Dv;
+      double sw1 = 0.0, bal1 = 0.0;
+      if (J < NSEGL) {
+        const char* p1 = p + kRecBytes;
+        A1 = rec_f4<RV_A>(p1); B1 = rec_f4<RV_B>(p1); C1 = rec_d2<RV_C>(p1); D1 = rec_d2<RV_D>(p1);
+        sw1 = SWa(J + 1); bal1 = BALa(J + 1);
+      }
+      const double2 Ev = rec_d2<RV_E>(p);                 // {B of the Newton solve, LOW at WP}
+      const double ul = (double)A.x, rs = (double)A.y, wp = (double)A.z, fc = (double)A.w;
+      const double rspan = Cv.x, kdt = Cv.y;
+      const double span = ul - rs;
+      const double Ej = (J <= 7) ? Ed[J] : 0.0;
+      const double DSUBj = has_sub ? (double)rec_tail(p).subin * DT : 0.0;
       // lower storage limit SWLIM and the drainage LOW at that limit; kind: 0 capillary
-      // (pre-pass), 1 wilting point, 2 field capacity, 3 porosity (frozen soil)
+      // equilibrium with the segment below, 1 wilting point, 2 field capacity, 3 porosity
+      // (frozen soil)
       int kind;
       if (J <= 7) {
         kind = (drin == 0.0 && J < NSEGL) ? 0 : 1;
@@ -339,11 +311,27 @@ __device__ __noinline__ void route_subprofile(const Image& img, int64_t s, const
       else if (J == NSEG && drin <= 0.0) kind = 2;
       else kind = 0;
       double swl, LOW;
-      if (kind == 0) { swl = (double)SWLc[J]; LOW = LOWc[J]; }
-      else if (kind == 1) { swl = wp; LOW = __ldg(&img.SD(SD_LOWWP, J, s)); }
-      else if (kind == 2) { swl = fc; LOW = __ldg(&img.SD(SD_LOWFC, J, s)); }
+      if (kind == 0) {
+        // F:4330-4340 == F:4356-4366: matric potential of J+1 (Brooks-Corey) carried to J,
+        // clipped to [WP, FC]; then LOW = K dt Theta(SWLIM)^C (F:4420-4421)
+        const double ul1 = (double)A1.x, rs1 = (double)A1.y, bub1 = (double)B1.y;
+        const double bub = (double)B.y, lam = (double)B.x;
+        const double base1 = sw1 + (bal1 / 2.0);
+        float RELSW = (float)fdiv_by(base1 - rs1, ul1 - rs1, C1.x);
+        if (RELSW < B1.z) RELSW = B1.z;
+        float PSIJP1 = (float)(bub1 * r8_pow((double)RELSW, D1.y));
+        if ((double)PSIJP1 < bub) PSIJP1 = (float)bub;
+        const float RELSWL = (float)r8_pow(bub / (double)PSIJP1, lam);
+        float SWLIM = (float)(((double)RELSWL * span) + rs);
+        if ((double)SWLIM < wp) SWLIM = (float)wp;
+        if ((double)SWLIM > fc) SWLIM = (float)fc;
+        swl = (double)SWLIM;
+        LOW = kdt * r8_pow(fdiv_by(swl - rs, span, rspan), Dv.x);
+      }
+      else if (kind == 1) { swl = wp; LOW = Ev.y; }
+      else if (kind == 2) { swl = fc; LOW = LOWFC_L; }
       else { swl = ul; LOW = kdt; }            // ((ul - rs)/(ul - rs))**C == 1
-      const double base = SW[J] + (BAL[J] / 2.0);                     // storage at the start of the step
+      const double base = swj + (balj / 2.0);                     // storage at the start of the step
 #ifdef HELP_DBG_SWEEP
       HELP_DBG_SWEEP
 #endif
@@ -353,33 +341,32 @@ __device__ __noinline__ void route_subprofile(const Image& img, int64_t s, const
           if (IBAR == 3) DRNMAX = 0.0;
           if (IBAR > 3) DRNMAX = DRNMAX + DSUBE;
           if (IBAR >= 3) {
-            DRIN[NSEGE + 1] = 0.0;
-            if (LAT == 0) { DRIN[NSEGL + 1] = 0.0; break; }
+            DRINa(NSEGE + 1) = 0.0;
+            if (LAT == 0) { DRINa(NSEGL + 1) = 0.0; break; }
           }
         }
         if (liner) {    // split the gravity water between leakage and lateral flow (F:4384-4413)
           double GRVWAT = DRNMAX + swl - fc;
           if (GRVWAT <= 0.0) {
-            DRIN[NSEGE + 1] = 0.0; DRIN[NSEGL + 1] = 0.0;
-            if (IBAR < 3) DRIN[NSEGE + 1] = DRIN[NSEGE + 1] + DSUBE;
+            DRINa(NSEGE + 1) = 0.0; DRINa(NSEGL + 1) = 0.0;
+            if (IBAR < 3) DRINa(NSEGE + 1) = DRINa(NSEGE + 1) + DSUBE;
           } else {
             if (GRVWAT >= ((QPERCY + QLATY) * DT)) {
-              DRIN[NSEGL + 1] = (QPERCY + QLATY) * DT;
-              DRIN[NSEGE + 1] = QPERCY * DT;
+              DRINa(NSEGL + 1) = (QPERCY + QLATY) * DT;
+              DRINa(NSEGE + 1) = QPERCY * DT;
             } else if (LAT == 0) {
-              DRIN[NSEGL + 1] = GRVWAT; DRIN[NSEGE + 1] = GRVWAT;
+              DRINa(NSEGL + 1) = GRVWAT; DRINa(NSEGE + 1) = GRVWAT;
             } else {
-              DRIN[NSEGL + 1] = GRVWAT;
+              DRINa(NSEGL + 1) = GRVWAT;
               const double QP = (GRVWAT / DT) * QPERCY / (QPERCY + QLATY);
-              DRIN[NSEGE + 1] = QP * DT;
+              DRINa(NSEGE + 1) = QP * DT;
             }
-            if (IBAR < 3) DRIN[NSEGE + 1] = DRIN[NSEGE + 1] + DSUBE;
+            if (IBAR < 3) DRINa(NSEGE + 1) = DRINa(NSEGE + 1) + DSUBE;
           }
           break;
         }
       }
       if (DRNMAX < 0.0) DRNMAX = 0.0;
-      const double span = ul - rs;
       const bool add_sub = (J == NSEGL && bottom && IBAR > 3);
       double out;
       if (LOW > DRNMAX) out = DRNMAX;
@@ -389,12 +376,12 @@ __device__ __noinline__ void route_subprofile(const Image& img, int64_t s, const
         if (SWMAX > ul) SWMAX = ul;
         if (SWMAX <= swl) out = 0.0;
         else {
-          const double C = __ldg(&img.SD(SD_C, J, s));
-          double HIGH = kdt * r8_pow((SWMAX - rs) / span, C);
+          const double C = Dv.x;
+          double HIGH = kdt * r8_pow(fdiv_by(SWMAX - rs, span, rspan), C);
           if (HIGH > DRNMAX) HIGH = DRNMAX;
           double SWMIN = SWMAX - HIGH;
           if (SWMIN < swl) SWMIN = swl;
-          LOW = kdt * r8_pow((SWMIN - rs) / span, C);
+          LOW = kdt * r8_pow(fdiv_by(SWMIN - rs, span, rspan), C);
           if (LOW > DRNMAX) LOW = DRNMAX;
           SWMAX = base + DSUBj + drin - Ej - LOW;
           if (add_sub) SWMAX = SWMAX + DSUBE;
@@ -402,18 +389,21 @@ __device__ __noinline__ void route_subprofile(const Image& img, int64_t s, const
           if (SWMAX <= SWMIN) out = DRNMAX;
           else {
             // Newton on f(x) = A - B x^C - 2x (F:4461-4488); B = K dt (1/(ul-rs))^C is a
-            // constant of the segment (set-up kernel)
-            double A = 2.0 * (SW[J] - rs) + BAL[J] + drin + DSUBj - Ej;
-            if (add_sub) A = A + (2.0 * DSUBE);
-            const double Bc = __ldg(&img.SD(SD_BC, J, s));
+            // constant of the segment (set-up kernel).  x^C and x^(C-1) share one logarithm.
+            double An = 2.0 * (swj - rs) + balj + drin + DSUBj - Ej;
+            if (add_sub) An = An + (2.0 * DSUBE);
+            const double Bc = Ev.x;
             const double TOLER = 0.003 * span;
             const double ftol = (double)0.3f * TOLER;
+            const double Cm1 = C - 1.0;
             double X0 = (SWMAX + SWMIN) / 2.0;
             int ITER;
             for (ITER = 1; ITER <= 100; ++ITER) {
-              const double FX0 = A - (Bc * r8_pow(X0, C)) - (2.0 * X0);
+              double pc, pc1;
+              r8_pow_sb(X0, C, Cm1, pc, pc1);
+              const double FX0 = An - (Bc * pc) - (2.0 * X0);
               if (FX0 <= ftol) break;
-              const double FX0DER = -(Bc * C * r8_pow(X0, C - 1.0)) - 2.0;
+              const double FX0DER = -(Bc * C * pc1) - 2.0;
               if (fabs(FX0DER) < 1.0e-03) break;
               const double DX = FX0 / FX0DER;
               X0 = X0 - DX;
@@ -422,24 +412,25 @@ __device__ __noinline__ void route_subprofile(const Image& img, int64_t s, const
             if (ITER > 100) flag |= kFlagNonConv;
             if (X0 > SWMAX) X0 = SWMAX;
             if (X0 < SWMIN) X0 = SWMIN;
-            out = 2.0 * (SW[J] - X0) + BAL[J] + drin + DSUBj - Ej;
+            out = 2.0 * (swj - X0) + balj + drin + DSUBj - Ej;
             if (bottom && IBAR > 3) out = out + DSUBE;
           }
         }
       }
-      const int above = __ldg(&img.SI(J, s));       // bit0: J above the drain layer, bit1: J+1 is
+      const int above = __float_as_int(B.w);        // bit0: J above the drain layer, bit1: J+1 is
       if (above & 1) { if (out > kdt) out = kdt; }
       if (out > DRNMAX) out = DRNMAX;
       if (out < 0.0) out = 0.0;
       if (J < NSEGL && (above & 2)) {
-        const double kdt1 = (double)__ldg(&img.SF(S_RC, J + 1, s)) * DT;
+        const double kdt1 = C1.y;
         if (out > kdt1) {
-          const double th = (double)__ldg(&img.SF(S_THICK, J, s)), th1 = (double)__ldg(&img.SF(S_THICK, J + 1, s));
-          const double ul1 = (double)__ldg(&img.SF(S_UL, J + 1, s)), sub1 = (double)__ldg(&img.SF(S_SUBIN, J + 1, s));
-          const float sw = (float)((base - rs) / span);
+          const RecTail t0 = rec_tail(p), t1 = rec_tail(p + kRecBytes);
+          const double th = (double)t0.thick, th1 = (double)t1.thick;
+          const double ul1 = (double)A1.x, sub1 = (double)t1.subin;
+          const float sw = (float)fdiv_by(base - rs, span, rspan);
           const float TRATIO = (float)(th / th1);
-          const double En = (J + 1 <= 7) ? (double)ET7[J + 1] * DT : 0.0;
-          double DRMX = ul1 - SW[J + 1] - (BAL[J + 1] / 2.0) + kdt1 + En - sub1 * DT;
+          const double En = (J + 1 <= 7) ? Ed[J + 1] : 0.0;
+          double DRMX = ul1 - sw1 - (bal1 / 2.0) + kdt1 + En - sub1 * DT;
           if (DRMX > DRNMAX) DRMX = DRNMAX;
           double DRNMX = kdt1 * (double)(1.0f + (sw * TRATIO));
           if (DRNMX > DRMX) DRNMX = DRMX;
@@ -448,36 +439,50 @@ __device__ __noinline__ void route_subprofile(const Image& img, int64_t s, const
           if (out < 0.0) out = 0.0;
         }
       }
-      DRIN[J + 1] = out;
+      DRINa(J + 1) = out;
+      A = A1; B = B1; Cv = C1; Dv = D1; swj = sw1; balj = bal1; drin = out;
     }
     // F:4518-4525 and PROFIL (F:4535-4574) fused: new balance bottom -> top, pushing
     // water above saturation into the segment above
-    if (IBAR == 3) DRIN[NSEGE + 1] = 0.0;
-    const double prc_step = DRIN[NSEGE + 1];
-    const double drn_step = liner ? (DRIN[NSEGL + 1] - DRIN[NSEGE + 1] + DSUBE) : 0.0;
+    if (IBAR == 3) DRINa(NSEGE + 1) = 0.0;
+    const double prc_step = DRINa(NSEGE + 1);
+    const double drn_step = liner ? (DRINa(NSEGL + 1) - DRINa(NSEGE + 1) + DSUBE) : 0.0;
     double EXC = 0.0;
-    for (int Kk = NSEGL; Kk >= NSEGB; --Kk) {
-      const double ul = (double)__ldg(&img.SF(S_UL, Kk, s));
-      const double sub = (double)__ldg(&img.SF(S_SUBIN, Kk, s)) * DT;
-      const double Ek = (Kk <= 7) ? (double)ET7[Kk] * DT : 0.0;
-      double BALT = DRIN[Kk] + sub - DRIN[Kk + 1] - Ek;
-      if (Kk == NSEGL && IBAR > 3) BALT = BALT + DSUBE;
-      const double DSW = SW[Kk] + ((BAL[Kk] + BALT) / 2.0);
-      const double S = DSW + EXC + (BALT / 2.0);
-      double EXCE = EXC;
-      if (EXCE < 0.0) EXCE = 0.0;
-      EXC = S - ul;
-      double newsw;
-      if (EXC > 0.0) {
-        BALT = ul - SW[Kk] - (BAL[Kk] / 2.0);
-        newsw = ul - (BALT / 2.0);
-      } else {
-        EXC = 0.0;
-        BALT = BALT + EXCE;
-        newsw = SW[Kk] + ((BAL[Kk] + BALT) / 2.0);
+    {
+      const char* pk = pL;
+      double dnext = DRINa(NSEGL + 1);
+      double din = DRINa(NSEGL), swk = SWa(NSEGL), balk = BALa(NSEGL);
+      float ulf = rec_f4<RV_A>(pk).x;
+      for (int Kk = NSEGL; Kk >= NSEGB; --Kk) {
+        const double sub = has_sub ? (double)rec_tail(pk).subin * DT : 0.0;
+        double din_n = 0.0, swk_n = 0.0, balk_n = 0.0;
+        float ulf_n = 0.0f;
+        if (Kk > NSEGB) {                        // the loads of the next segment up, ahead of their use
+          pk -= kRecBytes;
+          din_n = DRINa(Kk - 1); swk_n = SWa(Kk - 1); balk_n = BALa(Kk - 1); ulf_n = rec_f4<RV_A>(pk).x;
+        }
+        const double ul = (double)ulf;
+        const double Ek = (Kk <= 7) ? Ed[Kk] : 0.0;
+        double BALT = din + sub - dnext - Ek;
+        if (Kk == NSEGL && IBAR > 3) BALT = BALT + DSUBE;
+        const double DSW = swk + ((balk + BALT) / 2.0);
+        const double S = DSW + EXC + (BALT / 2.0);
+        double EXCE = EXC;
+        if (EXCE < 0.0) EXCE = 0.0;
+        EXC = S - ul;
+        double newsw;
+        if (EXC > 0.0) {
+          BALT = ul - swk - (balk / 2.0);
+          newsw = ul - (BALT / 2.0);
+        } else {
+          EXC = 0.0;
+          BALT = BALT + EXCE;
+          newsw = swk + ((balk + BALT) / 2.0);
+        }
+        SWa(Kk) = newsw;
+        BALa(Kk) = BALT;
+        dnext = din; din = din_n; swk = swk_n; balk = balk_n; ulf = ulf_n;
       }
-      SW[Kk] = newsw;
-      BAL[Kk] = BALT;
     }
     EXCESS = EXC;
     EXTRA = (float)EXCESS;
@@ -517,7 +522,7 @@ struct Surf {      // REAL*4 surface-process state of one cell
 #define HELP_SIM_THREADS 128
 #endif
 #ifndef HELP_SIM_MINBLOCKS
-#define HELP_SIM_MINBLOCKS 6
+#define HELP_SIM_MINBLOCKS 5
 #endif
 #ifndef HELP_SIM_NO_DAYSYNC
 #define HELP_SIM_DAYSYNC 1
@@ -578,7 +583,7 @@ __global__ void __launch_bounds__(HELP_SIM_THREADS, HELP_SIM_MINBLOCKS) help_sim
       ProfC& p = PR[N];
       const int ns = img.PI(Q_NSEGN, N, s);
       p.n = N; p.NSEGB = e + 1; p.NSEGE = e + ns; p.NSEG = NSEG;
-      p.nstep = img.PI(Q_NSTEP, N, s); p.ibar = img.PI(Q_IBAR, N, s); p.lat = img.PI(Q_LAT, N, s);
+      p.nstep = img.PI(Q_NSTEP, N, s); p.ibar = img.PI(Q_IBAR, N, s); p.lat = img.PI(Q_LAT, N, s); p.subin = img.PI(Q_SUBIN, N, s);
       p.drculs = img.PF(P_DRCULS, N, s); p.dthics = img.PF(P_DTHICS, N, s);
       p.slope = img.PF(P_SLOPE, N, s); p.xleng = img.PF(P_XLENG, N, s); p.sublin = img.PF(P_SUBLIN, N, s);
       p.fml.lcase = img.PI(Q_LCASE, N, s); p.fml.lpq = img.PI(Q_LPQ, N, s); p.fml.ltype = img.PI(Q_LTYPE, N, s);
@@ -591,21 +596,23 @@ __global__ void __launch_bounds__(HELP_SIM_THREADS, HELP_SIM_MINBLOCKS) help_sim
     }
   }
   // ---- state (run_simulation F:200-317; READIN F:1344-1351; INITIA F:2437-2442) ---------------
-  // segment state in shared memory: the per-thread working set of all resident cells is far
-  // larger than L1, so thread-local arrays were evicted to L2/HBM between sub-steps.  One row
-  // per thread, odd row length (in doubles) = conflict-free 64-bit accesses.
+  // Segment state.  HELP_SIM_STATE_SMEM keeps SW/BAL in shared memory, [segment][thread]
+  // (stride blockDim.x, conflict-free 64-bit accesses), where the streaming of the routing
+  // records through L1 cannot evict it; otherwise the arrays are thread-local (L1-cached).
 #ifdef HELP_SIM_STATE_SMEM
   extern __shared__ double state_smem[];
-  constexpr int SSTR = (MAXSEG + 2) | 1;
-  double* SW = state_smem + (int)threadIdx.x * SSTR;
-  double* BAL = state_smem + ((int)blockDim.x + (int)threadIdx.x) * SSTR;
-  double DRIN[MAXSEG + 3], LOWc[MAXSEG + 2];
+  double* SW = state_smem + threadIdx.x;
+  double* BAL = state_smem + (size_t)(MAXSEG + 2) * blockDim.x + threadIdx.x;
+#ifdef HELP_SIM_DRIN_SMEM
+  double* DRIN = state_smem + (size_t)2 * (MAXSEG + 2) * blockDim.x + threadIdx.x;
 #else
-  double SW[MAXSEG + 2], BAL[MAXSEG + 2], DRIN[MAXSEG + 3], LOWc[MAXSEG + 2];
+  double DRIN[MAXSEG + 3];
 #endif
-  float SWLc[MAXSEG + 2];
-  for (int J = 1; J <= NSEG; ++J) { SW[J] = (double)img.SF(S_SW0, J, s); BAL[J] = 0.0; }
-  SW[0] = BAL[0] = 0.0; SW[NSEG + 1] = BAL[NSEG + 1] = 0.0;
+#else
+  double SW[MAXSEG + 2], BAL[MAXSEG + 2], DRIN[MAXSEG + 3];
+#endif
+  for (int J = 1; J <= NSEG; ++J) { SWa(J) = (double)img.SF(S_SW0, J, s); BALa(J) = 0.0; }
+  SWa(0) = 0.0; BALa(0) = 0.0; SWa(NSEG + 1) = 0.0; BALa(NSEG + 1) = 0.0;
   Surf U;
   U.RUN = 0.f; U.ES1T = 0.f; U.TS2 = 0.f; U.ADDRUN = 0.f;
   for (int J = 0; J < 8; ++J) U.ET[J] = 0.f;
@@ -653,8 +660,8 @@ __global__ void __launch_bounds__(HELP_SIM_THREADS, HELP_SIM_MINBLOCKS) help_sim
     if (IPRE >= 2) {
       U.ADDRUN = 0.0f;
       for (int k = 2; k <= 6; ++k) EXWAT[k] = 0.0f;
-      if (IPRE == 3) for (int J = 1; J <= NSEG; ++J) SW[J] = (double)img.SF(S_SW0, J, s);
-      for (int J = 1; J <= NSEG; ++J) BAL[J] = 0.0;
+      if (IPRE == 3) for (int J = 1; J <= NSEG; ++J) SWa(J) = (double)img.SF(S_SW0, J, s);
+      for (int J = 1; J <= NSEG; ++J) BALa(J) = 0.0;
     }
     const bool report = (IPRE >= 2);
     const int npass_years = report ? NY : 1;
@@ -866,7 +873,7 @@ __global__ void __launch_bounds__(HELP_SIM_THREADS, HELP_SIM_MINBLOCKS) help_sim
             float WTSM = 0.0f;
 #pragma unroll
             for (int I = 1; I <= 7; ++I) {
-              const float swul = (float)SW[I];
+              const float swul = (float)SWa(I);
               float sw = swul;
               const float SWAMCI = (FCf[I] + WPf[I]) / 2.0f;
               if (swul > ULf[I]) sw = ULf[I];
@@ -1098,8 +1105,8 @@ __global__ void __launch_bounds__(HELP_SIM_THREADS, HELP_SIM_MINBLOCKS) help_sim
               for (int J = 1; J <= 7; ++J) {
                 XP[J] = 0.0f; ESJ[J] = 0.0f;
                 ULL[J] = FCf[J] - WPf[J];
-                // SWUL(J) is the REAL*4 mirror of DSWUL(J) (F:666-668); DCHG(J) == BAL[J]
-                ST[J] = (float)((double)(float)SW[J] + (BAL[J] / 2.0) - (double)WPf[J] + (double)DRINF);
+                // SWUL(J) is the REAL*4 mirror of DSWUL(J) (F:666-668); DCHG(J) == BALa(J)
+                ST[J] = (float)((double)(float)SWa(J) + (BALa(J) / 2.0) - (double)WPf[J] + (double)DRINF);
                 if (ST[J] < 0.0f) ST[J] = 0.0f;
                 if (ST[J] > ULf[J]) { XPINF = ST[J] - ULf[J]; ST[J] = ULf[J]; }
                 else XPINF = 0.0f;
@@ -1191,15 +1198,15 @@ __global__ void __launch_bounds__(HELP_SIM_THREADS, HELP_SIM_MINBLOCKS) help_sim
 #ifdef HELP_DBG_PRE
         HELP_DBG_PRE
 #endif
-        route_subprofile<MAXSEG>(img, s, PR[1], U.PINF, U.ET, U.IFREZ, SW, BAL, DRIN, SWLc, LOWc, DRN[1], PRC[1], U.ADDRUN, flag);
+        route_subprofile<MAXSEG>(img, s, PR[1], U.PINF, U.ET, U.IFREZ, SW, BAL, DRIN, DRN[1], PRC[1], U.ADDRUN, flag);
         {
           float EXET = 0.0f;
 #pragma unroll
           for (int J = 1; J <= 7; ++J) {
             const double wp = (double)WPf[J];
-            if ((SW[J] + (BAL[J] / 2.0)) < wp) {
-              const float EXET2 = (float)((double)EXET + wp - SW[J] - (BAL[J] / 2.0));
-              if (EXET <= U.ETT) { SW[J] = wp - (BAL[J] / 2.0); EXET = EXET2; }
+            if ((SWa(J) + (BALa(J) / 2.0)) < wp) {
+              const float EXET2 = (float)((double)EXET + wp - SWa(J) - (BALa(J) / 2.0));
+              if (EXET <= U.ETT) { SWa(J) = wp - (BALa(J) / 2.0); EXET = EXET2; }
             }
           }
           U.RUN = U.RUN + U.ADDRUN * FRUNOF;
@@ -1224,7 +1231,7 @@ __global__ void __launch_bounds__(HELP_SIM_THREADS, HELP_SIM_MINBLOCKS) help_sim
           const float FINn = (float)(PRC[N - 1] + (double)EXWAT[N]);
           if (N > nprof) break;
           EXWAT[N] = 0.0f;
-          route_subprofile<MAXSEG>(img, s, PR[N], FINn, U.ET, U.IFREZ, SW, BAL, DRIN, SWLc, LOWc, DRN[N], PRC[N], EXWAT[N], flag);
+          route_subprofile<MAXSEG>(img, s, PR[N], FINn, U.ET, U.IFREZ, SW, BAL, DRIN, DRN[N], PRC[N], EXWAT[N], flag);
           if (N <= 5) {
             if (LDn[N] > 0) {
               const double RCR = (double)RECIR[N] * DRN[N] / (double)100.0f;
@@ -1281,7 +1288,7 @@ __global__ void __launch_bounds__(HELP_SIM_THREADS, HELP_SIM_MINBLOCKS) help_sim
       U.OLDSNO = U.ADDRUN + U.SNO;
       if (IPRE < 2) {
         IPRE = IPRE + 2;
-        for (int J = 1; J <= NSEG; ++J) { SW[J] = SW[J] + BAL[J] / 2.0; BAL[J] = 0.0; }
+        for (int J = 1; J <= NSEG; ++J) { SWa(J) = SWa(J) + BALa(J) / 2.0; BALa(J) = 0.0; }
         break;
       }
     }   // year

@@ -19,12 +19,14 @@ static thread_local dim3s blockIdx{0, 0, 0}, threadIdx{0, 0, 0}, blockDim{1, 1, 
 template <typename T> static inline T __ldg(const T* p) { return *p; }
 static inline float __int_as_float(int i) { float f; std::memcpy(&f, &i, 4); return f; }
 static inline int __float_as_int(float f) { int i; std::memcpy(&i, &f, 4); return i; }
-struct float4 { float x, y, z, w; }; struct double2 { double x, y; };
+struct float4 { float x, y, z, w; }; struct double2 { double x, y; }; struct float2 { float x, y; };
+static inline float2 make_float2(float x, float y) { return float2{x, y}; }
 static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
 static inline double2 make_double2(double x, double y) { return double2{x, y}; }
 static inline unsigned __ballot_sync(unsigned, int p) { return p ? 1u : 0u; }
 static inline int __any_sync(unsigned, int p) { return p; }
 static inline unsigned __activemask() { return 1u; }
+static inline void __syncthreads() {}
 static inline float __fmul_rn(float a, float b) { return a * b; }
 static inline float __fadd_rn(float a, float b) { return a + b; }
 #include <math.h>
@@ -46,6 +48,7 @@ static inline float r4_pow7(float x) { return powf(x, 7.f); }
 static inline float r4_pow4(float x) { return powf(x, 4.f); }
 static inline double r8_pow(double x, double y) { return pow(x, y); }
 static inline void r8_pow2(double x0, double y0, double x1, double y1, double& r0, double& r1) { r0 = pow(x0, y0); r1 = pow(x1, y1); }
+static inline void r8_pow_sb(double x, double y0, double y1, double& r0, double& r1) { r0 = pow(x, y0); r1 = pow(x, y1); }
 static inline double r8_log(double x) { return log(x); }
 static inline double r8_atan(double x) { return atan(x); }
 static inline double r8_sin(double x) { return sin(x); }
@@ -72,6 +75,7 @@ static long long g_cap[8]; static float g_prev_relsw[128];
 #define HELP_DBG_CAP { g_cap[0]++; if (RELSW == RELMIN) g_cap[1]++; if ((double)PSIJP1 == c.bub) g_cap[2]++; if ((double)SWLIM == c.wp) g_cap[3]++; if ((double)SWLIM == c.fc) g_cap[4]++; if (RELSW == g_prev_relsw[J]) g_cap[5]++; g_prev_relsw[J] = RELSW; }
 #define r8_pow(x, y) (g_pow_count[__LINE__ & 4095]++, helpmath::det_pow(x, y))
 #define r8_pow2(x0, y0, x1, y1, r0, r1) (g_pow_count[__LINE__ & 4095] += 2, helpmath::det_pow2(x0, y0, x1, y1, r0, r1))
+#define r8_pow_sb(x, y0, y1, r0, r1) (g_pow_count[__LINE__ & 4095] += 2, helpmath::det_pow_samebase(x, y0, y1, r0, r1))
 #endif
 
 #ifdef HELP_EMU_MEMO   // per-cell event streams: would a memo of the previous evaluation have hit?

@@ -30,8 +30,8 @@ extern "C" int emu_run(const help_b200_batch* b, float* monthly, float* yearly, 
   int segcap = 7 + 3 * b->max_layers; if (segcap > 67) segcap = 67;
   int64_t stride = ((n + 31) / 32) * 32;
   std::vector<float> f32(Image::n_f32(segcap) * stride); std::vector<int32_t> i32(Image::n_i32(segcap) * stride); std::vector<double> f64(Image::n_f64(segcap) * stride);
-  std::vector<float4> r4((size_t)segcap * kRecF * stride); std::vector<double2> rd((size_t)segcap * kRecD * stride);
-  Image img{f32.data(), i32.data(), f64.data(), stride, segcap, r4.data(), rd.data()};
+  std::vector<char> rec((size_t)Image::rec_bytes(stride, segcap));
+  Image img{f32.data(), i32.data(), f64.data(), stride, segcap, rec.data()};
   for (int64_t c = 0; c < n; ++c) { blockIdx.x = (unsigned)c; help_setup_kernel(B, img, nullptr, flags, topo, nullptr); }
   SimArgs A; A.img = img; A.pre = pre.data(); A.tmp = tmp.data(); A.rad = rad.data(); A.years = b->years; A.n_years = ny; A.n_cells = n; A.perm = nullptr;
   A.monthly = monthly; A.yearly = yearly; A.raw = raw; A.flags = flags;
