@@ -73,7 +73,8 @@ def _load(libm: str = "det"):
 
 MATH_FN = {"pow": 0, "exp": 1, "log": 2, "sin": 3, "cos": 4, "atan": 5, "r4_acos": 6, "r4_tan": 7,
            "r4_pow": 8, "r4_exp": 9, "r4_log": 10, "r4_sin": 11, "r4_cos": 12, "r4_log10": 13,
-           "r4_sqrt": 14, "r4_pow8": 15, "r4_pow7": 16, "r4_pow4": 17, "pow2": 18}
+           "r4_sqrt": 14, "r4_pow8": 15, "r4_pow7": 16, "r4_pow4": 17, "pow2": 18,
+           "pow_sb": 19, "fdiv": 20}
 
 
 def math_eval(fn: str, x, y=None, libm: str = "det") -> np.ndarray:

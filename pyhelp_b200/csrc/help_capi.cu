@@ -244,7 +244,23 @@ extern "C" int help_b200_engine_create(const help_b200_batch* b, int want_monthl
 #undef CUB_
 }
 
-template <int MAXSEG>
+// Resident blocks per SM for a batch that needs k = ceil(blocks / SMs) of them: the fewest
+// waves the 80-register build (6 blocks) allows, filled evenly, never below the 128-register
+// build (4 blocks).  HELP_B200_MINB overrides (developer A/B runs).
+static int pick_minb(int64_t n, int device) {
+  if (const char* f = getenv("HELP_B200_MINB")) { const int v = atoi(f); if (v >= 4 && v <= 6) return v; }
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  const int64_t blocks = (n + HELP_SIM_THREADS - 1) / HELP_SIM_THREADS;
+  const int64_t k = (blocks + sms - 1) / sms;
+  const int64_t waves = (k + 5) / 6;
+  int64_t m = (k + waves - 1) / waves;
+  if (m < 4) m = 4;
+  if (m > 6) m = 6;
+  return (int)m;
+}
+
+template <int MAXSEG, int MINB>
 static void launch_sim(const SimArgs& A, int64_t n, cudaStream_t st) {
   const int th = HELP_SIM_THREADS;
 #ifdef HELP_SIM_STATE_SMEM
@@ -253,11 +269,11 @@ static void launch_sim(const SimArgs& A, int64_t n, cudaStream_t st) {
 #else
   const size_t smem = (size_t)2 * th * (MAXSEG + 2) * sizeof(double);
 #endif
-  cudaFuncSetAttribute(help_sim_kernel<MAXSEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaFuncSetAttribute(help_sim_kernel<MAXSEG, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 #else
   const size_t smem = 0;
 #endif
-  help_sim_kernel<MAXSEG><<<(unsigned)((n + th - 1) / th), th, smem, st>>>(A);
+  help_sim_kernel<MAXSEG, MINB><<<(unsigned)((n + th - 1) / th), th, smem, st>>>(A);
 }
 
 extern "C" int help_b200_engine_simulate(help_b200_engine* e, void* stream) {
@@ -285,10 +301,20 @@ extern "C" int help_b200_engine_simulate(help_b200_engine* e, void* stream) {
     A.n_years = e->ny; A.n_cells = n; A.perm = perm;
     A.monthly = e->d_monthly; A.yearly = e->d_yearly; A.raw = e->d_raw; A.flags = e->d_flags;
     switch (e->maxseg_t) {
-      case 16: launch_sim<16>(A, n, st); break;
-      case 25: launch_sim<25>(A, n, st); break;
-      case 40: launch_sim<40>(A, n, st); break;
-      default: launch_sim<67>(A, n, st); break;
+      case 16:
+        switch (pick_minb(n, e->device)) {
+          case 6: launch_sim<16, 6>(A, n, st); break;
+          case 5: launch_sim<16, 5>(A, n, st); break;
+          default: launch_sim<16, 4>(A, n, st); break;
+        }
+        break;
+#ifndef HELP_DEV_FAST_BUILD
+      case 25: launch_sim<25, 4>(A, n, st); break;
+      case 40: launch_sim<40, 4>(A, n, st); break;
+      default: launch_sim<67, 4>(A, n, st); break;
+#else
+      default: return fail(HELP_B200_EINVAL, "developer build: MAXSEG 16 only");
+#endif
     }
     e->n_launches += 1;
   } else {
@@ -373,13 +399,15 @@ __global__ void math_eval_kernel(int fn, const double* __restrict__ x, const dou
     case 16: r = r4_pow7(af); break;
     case 17: r = r4_pow4(af); break;
     case 18: { double r0, r1; helpmath::det_pow2(a, b, b == 0.0 ? 1.5 : 1.0 / b, a, r0, r1); r = r0; break; }
+    case 19: { double r0, r1; helpmath::det_pow_samebase(a, b - 1.0, b, r0, r1); r = r1; break; }
+    case 20: { const double q = a / b; r = helpmath::div_by_const(a, b, 1.0 / b); if (q != q) r = q; break; }
     default: break;
   }
   out[i] = r;
 }
 
 extern "C" int help_b200_math_eval(int fn, const double* x, const double* y, double* out, int64_t n) {
-  if (fn < 0 || fn > 18 || !x || !out || n < 0) return fail(HELP_B200_EINVAL, "math_eval: bad argument");
+  if (fn < 0 || fn > 20 || !x || !out || n < 0) return fail(HELP_B200_EINVAL, "math_eval: bad argument");
   if (help_b200_device_count() < 1) return fail(HELP_B200_ENODEV, "no CUDA device (this engine has no CPU path)");
   if (n == 0) return 0;
   double *dx = nullptr, *dy = nullptr, *d_out = nullptr;

@@ -210,25 +210,13 @@ __host__ __device__ __forceinline__ double r8_sqrt(double x) { return helpmath::
 #endif
 
 
-// a / b, correctly rounded, given rb = RN(1/b) (a constant of the segment).  q0 = RN(a rb) is
-// within 2 ulp of a/b; one residual correction makes it faithful, and a second one gives
-// RN(a/b) exactly (Markstein's theorem: y = RN(1/b), q faithful, r = a - b q exact
-// => RN(q + r y) = RN(a/b)).  Same bits as the IEEE division the reference executes, at 5
-// FP64 operations instead of the ~15 + slow-path test of div.rn.f64.  Domain: b, 1/b, a/b
-// finite and normal (or a = 0); tests/test_help_math.py checks it against '/'.
+// a / b through the correctly rounded reciprocal of b (help_math.h div_by_const): the bits of
+// the IEEE division, 5 FP64 operations.  The glibc-libm emulator build divides directly.
 __host__ __device__ __forceinline__ double fdiv_by(double a, double b, double rb) {
-#if defined(__CUDA_ARCH__)
-  double q = __dmul_rn(a, rb);
-  double r = __fma_rn(-q, b, a);
-  q = __fma_rn(r, rb, q);
-  r = __fma_rn(-q, b, a);
-  return __fma_rn(r, rb, q);
+#ifdef HELP_R4_OVERRIDE
+  (void)rb; return a / b;
 #else
-  double q = a * rb;
-  double r = __builtin_fma(-q, b, a);
-  q = __builtin_fma(r, rb, q);
-  r = __builtin_fma(-q, b, a);
-  return __builtin_fma(r, rb, q);
+  return helpmath::div_by_const(a, b, rb);
 #endif
 }
 

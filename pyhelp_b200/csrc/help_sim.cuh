@@ -515,20 +515,21 @@ struct Surf {      // REAL*4 surface-process state of one cell
 };
 
 // Block shape.  Every warp of a block is kept in the same day of the simulation by one
-// barrier per day (HELP_SIM_DAYSYNC): the routing code is several times larger than the
-// 32 KB L1.5 instruction cache, and warps that run the same region together share its fetches
-// (measured on B200: +15 % throughput, profiles/r1_notes.md).
+// barrier per day (HELP_SIM_DAYSYNC): the routing code is larger than the 32 KB L1.5
+// instruction cache, and warps that run the same region together share its fetches
+// (measured on B200: +12 % throughput, profiles/r1_notes.md).
+// The kernel is compiled for several register budgets (MINB = resident blocks of
+// HELP_SIM_THREADS threads per SM: 4 -> 128 registers, 5 -> 96, 6 -> 80): all cells of a launch
+// take the same time, so the launcher (help_capi.cu pick_minb) chooses the budget that fits
+// the batch into the fewest, evenly filled waves.
 #ifndef HELP_SIM_THREADS
 #define HELP_SIM_THREADS 128
-#endif
-#ifndef HELP_SIM_MINBLOCKS
-#define HELP_SIM_MINBLOCKS 5
 #endif
 #ifndef HELP_SIM_NO_DAYSYNC
 #define HELP_SIM_DAYSYNC 1
 #endif
-template <int MAXSEG>
-__global__ void __launch_bounds__(HELP_SIM_THREADS, HELP_SIM_MINBLOCKS) help_sim_kernel(SimArgs A) {
+template <int MAXSEG, int MINB>
+__global__ void __launch_bounds__(HELP_SIM_THREADS, MINB) help_sim_kernel(SimArgs A) {
   const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= A.n_cells) return;
   const Image& img = A.img;

@@ -63,6 +63,31 @@ def test_dual_pow_returns_the_same_bits():
     assert np.array_equal(a.view(np.uint64), b.view(np.uint64))
 
 
+def test_shared_logarithm_pow_returns_the_same_bits():
+    """det_pow_samebase (x**(y-1) and x**y from one logarithm: the Newton step of the drainage
+    solve, pyhelp/HELP3O.FOR:4470-4473) == det_pow"""
+    x = np.concatenate([G["pow_x"], [0.0, -1.0, 1.0, 1e-320, np.inf, 2.0, 1e-5]])
+    y = np.concatenate([G["pow_y"], [2.0, 2.0, 7.0, 0.5, 0.5, 1e200, 200.0]])
+    a = oracle.math_eval("pow", x, y)
+    b = oracle.math_eval("pow_sb", x, y)
+    assert np.array_equal(a.view(np.uint64), b.view(np.uint64))
+
+
+def test_division_through_the_rounded_reciprocal_is_the_ieee_quotient():
+    """div_by_const(a, b, RN(1/b)) == a / b bit for bit: the routing loop divides by the
+    segment constant UL-RS this way (help_image.h fdiv_by)"""
+    rng = np.random.default_rng(3)
+    n = 2_000_000
+    b = np.concatenate([rng.uniform(1e-3, 60.0, n), rng.uniform(0.5, 1.0, n).astype(np.float32).astype(np.float64)])
+    a = np.concatenate([rng.uniform(-5.0, 60.0, n), rng.uniform(0.0, 1.0, n) * b[n:]])
+    # mantissas of all ones / few bits, exact quotients, zero numerators
+    b[:1000] = np.nextafter(2.0 ** rng.integers(-8, 6, 1000), 0.0)
+    a[1000:2000] = b[1000:2000] * rng.integers(1, 1 << 20, 1000)
+    a[2000:2100] = 0.0
+    got = oracle.math_eval("fdiv", a, b)
+    assert np.array_equal(got.view(np.uint64), (a / b).view(np.uint64))
+
+
 def test_glibc_build_differs_only_in_last_place():
     """the second oracle build uses the host libm; same functions to within an ulp or two"""
     a = oracle.math_eval("pow", G["pow_x"][:500], G["pow_y"][:500])
@@ -78,7 +103,10 @@ def test_device_functions_match_cpu_bits(fn):
     from pyhelp_b200 import _native as N
     rng = np.random.default_rng(7)
     n = 200_000
-    if fn in ("pow", "r4_pow", "pow2"):
+    if fn == "fdiv":
+        x = np.concatenate([rng.uniform(-5.0, 60.0, n // 2), rng.uniform(0.0, 1.0, n // 2)])
+        y = np.concatenate([rng.uniform(1e-3, 60.0, n // 2), rng.uniform(0.5, 1.0, n // 2).astype(np.float32).astype(np.float64)])
+    elif fn in ("pow", "r4_pow", "pow2", "pow_sb"):
         x = np.concatenate([rng.uniform(1e-6, 1.0, n // 2), 10 ** rng.uniform(-12, 4, n // 2)])
         y = np.concatenate([rng.uniform(0.01, 60.0, n // 2), rng.uniform(-40, 40, n // 2)])
     elif fn in ("exp", "r4_exp"):
