@@ -103,7 +103,8 @@ enum ImgPI : int {
   Q_LPQ,         // LPQ(n)
   Q_LTYPE,       // LAYER(LP(n)) (F:5292)
   Q_LD,          // LD(n)
-  Q_SUBIN,       // 1 if any segment of the subprofile has subsurface inflow (SUBINS > 0)
+  Q_SUBIN,       // bit0: a segment of the subprofile has subsurface inflow (SUBINS > 0);
+                 // bit1: "plain" subprofile: IBAR = 0, no inflow, not above a drain layer
   Q_NF
 };
 // i32 per segment: bit0 = LAYSEG(J,2) < LD(NPROF) (F:4494), bit1 = the same for J+1 (F:4499)

@@ -698,9 +698,13 @@ help_setup_kernel(BatchDev B, Image img, const int32_t* __restrict__ perm, uint3
     }
     int e2 = 0;
     for (int N = 1; N <= 6; ++N) {
-      int any = 0;
-      for (int J = e2 + 1; J <= e2 + S.NSEGn[N]; ++J) if (img.SF(S_SUBIN, J, slot) != 0.0f) any = 1;
-      img.PI(Q_SUBIN, N, slot) = any;
+      int any = 0, flg = 0;
+      for (int J = e2 + 1; J <= e2 + S.NSEGn[N]; ++J) {
+        if (img.SF(S_SUBIN, J, slot) != 0.0f) any = 1;
+        flg |= img.SI(J, slot);
+      }
+      const int plain = (img.PI(Q_IBAR, N, slot) == 0 && !any && flg == 0 && img.PF(P_SUBLIN, N, slot) == 0.0f) ? 2 : 0;
+      img.PI(Q_SUBIN, N, slot) = any | plain;
       e2 += S.NSEGn[N];
     }
   }

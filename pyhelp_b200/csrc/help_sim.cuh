@@ -226,20 +226,25 @@ struct ProfC {
 #define DRINa(j) DRIN[(j)]
 #endif
 
-template <int MAXSEG>
+// PLAIN = the subprofile has no liner (IBAR = 0), no subsurface inflow and no lateral-drain
+// layer below it (every natural-soil profile of a PyHELP grid): the liner, lateral-drainage
+// and inflow terms fold away at compile time.  Adding the inflow term 0.0 is the identity
+// there (none of the partial sums can be -0.0), so it is dropped too.
+template <int MAXSEG, bool PLAIN>
 __device__ __noinline__ void route_subprofile(const Image& img, int64_t s, const ProfC& P, float FIN,
                                               const float* __restrict__ ET7, int IFREZ,
                                               double* __restrict__ SW, double* __restrict__ BAL,
                                               double* __restrict__ DRIN, double& DRNo, double& PRCo,
                                               float& EXTRA, uint32_t& flag) {
-  const int NSEGB = P.NSEGB, NSEGE = P.NSEGE, NSEG = P.NSEG, IBAR = P.ibar, LAT = P.lat;
+  const int NSEGB = P.NSEGB, NSEGE = P.NSEGE, NSEG = P.NSEG;
+  const int IBAR = PLAIN ? 0 : P.ibar, LAT = PLAIN ? 0 : P.lat;
   const int NSEGL = (IBAR == 0 || IBAR == 3) ? NSEGE : NSEGE - 1;
   const double DT = 1.0 / (double)P.nstep;
   const double F = (double)FIN * DT;
-  const double DSUBE = (double)P.sublin * DT;            // DSUB(NSEGE)
+  const double DSUBE = PLAIN ? 0.0 : (double)P.sublin * DT;            // DSUB(NSEGE)
   const bool bottom = (NSEGE == NSEG);
   const bool liner = !(IBAR == 0 || IBAR == 3);
-  const bool has_sub = (P.subin != 0);
+  const bool has_sub = PLAIN ? false : ((P.subin & 1) != 0);
   const char* const p0 = img.rec_p(s) + (int64_t)(NSEGB - 1) * kRecBytes;
   const char* const pL = p0 + (int64_t)(NSEGL - NSEGB) * kRecBytes;
   const double LOWFC_L = rec_tail(pL).lowfc;            // SWLIM = FC occurs at segment NSEGL only
@@ -335,7 +340,7 @@ __device__ __noinline__ void route_subprofile(const Image& img, int64_t s, const
 #ifdef HELP_DBG_SWEEP
       HELP_DBG_SWEEP
 #endif
-      double DRNMAX = base + drin + DSUBj - Ej - swl;
+      double DRNMAX = PLAIN ? (base + drin - Ej - swl) : (base + drin + DSUBj - Ej - swl);
       if (J == NSEGL) {
         if (bottom) {
           if (IBAR == 3) DRNMAX = 0.0;
@@ -371,7 +376,7 @@ __device__ __noinline__ void route_subprofile(const Image& img, int64_t s, const
       double out;
       if (LOW > DRNMAX) out = DRNMAX;
       else {
-        double SWMAX = base + DSUBj + drin - Ej;
+        double SWMAX = PLAIN ? (base + drin - Ej) : (base + DSUBj + drin - Ej);
         if (add_sub) SWMAX = SWMAX + DSUBE;
         if (SWMAX > ul) SWMAX = ul;
         if (SWMAX <= swl) out = 0.0;
@@ -383,14 +388,14 @@ __device__ __noinline__ void route_subprofile(const Image& img, int64_t s, const
           if (SWMIN < swl) SWMIN = swl;
           LOW = kdt * r8_pow(fdiv_by(SWMIN - rs, span, rspan), C);
           if (LOW > DRNMAX) LOW = DRNMAX;
-          SWMAX = base + DSUBj + drin - Ej - LOW;
+          SWMAX = PLAIN ? (base + drin - Ej - LOW) : (base + DSUBj + drin - Ej - LOW);
           if (add_sub) SWMAX = SWMAX + DSUBE;
           if (SWMAX > ul) SWMAX = ul;
           if (SWMAX <= SWMIN) out = DRNMAX;
           else {
             // Newton on f(x) = A - B x^C - 2x (F:4461-4488); B = K dt (1/(ul-rs))^C is a
             // constant of the segment (set-up kernel).  x^C and x^(C-1) share one logarithm.
-            double An = 2.0 * (swj - rs) + balj + drin + DSUBj - Ej;
+            double An = PLAIN ? (2.0 * (swj - rs) + balj + drin - Ej) : (2.0 * (swj - rs) + balj + drin + DSUBj - Ej);
             if (add_sub) An = An + (2.0 * DSUBE);
             const double Bc = Ev.x;
             const double TOLER = 0.003 * span;
@@ -412,12 +417,12 @@ __device__ __noinline__ void route_subprofile(const Image& img, int64_t s, const
             if (ITER > 100) flag |= kFlagNonConv;
             if (X0 > SWMAX) X0 = SWMAX;
             if (X0 < SWMIN) X0 = SWMIN;
-            out = 2.0 * (swj - X0) + balj + drin + DSUBj - Ej;
+            out = PLAIN ? (2.0 * (swj - X0) + balj + drin - Ej) : (2.0 * (swj - X0) + balj + drin + DSUBj - Ej);
             if (bottom && IBAR > 3) out = out + DSUBE;
           }
         }
       }
-      const int above = __float_as_int(B.w);        // bit0: J above the drain layer, bit1: J+1 is
+      const int above = PLAIN ? 0 : __float_as_int(B.w);        // bit0: J above the drain layer, bit1: J+1 is
       if (above & 1) { if (out > kdt) out = kdt; }
       if (out > DRNMAX) out = DRNMAX;
       if (out < 0.0) out = 0.0;
@@ -463,7 +468,7 @@ __device__ __noinline__ void route_subprofile(const Image& img, int64_t s, const
         }
         const double ul = (double)ulf;
         const double Ek = (Kk <= 7) ? Ed[Kk] : 0.0;
-        double BALT = din + sub - dnext - Ek;
+        double BALT = PLAIN ? (din - dnext - Ek) : (din + sub - dnext - Ek);
         if (Kk == NSEGL && IBAR > 3) BALT = BALT + DSUBE;
         const double DSW = swk + ((balk + BALT) / 2.0);
         const double S = DSW + EXC + (BALT / 2.0);
@@ -1199,7 +1204,8 @@ __global__ void __launch_bounds__(HELP_SIM_THREADS, MINB) help_sim_kernel(SimArg
 #ifdef HELP_DBG_PRE
         HELP_DBG_PRE
 #endif
-        route_subprofile<MAXSEG>(img, s, PR[1], U.PINF, U.ET, U.IFREZ, SW, BAL, DRIN, DRN[1], PRC[1], U.ADDRUN, flag);
+        if (PR[1].subin & 2) route_subprofile<MAXSEG, true>(img, s, PR[1], U.PINF, U.ET, U.IFREZ, SW, BAL, DRIN, DRN[1], PRC[1], U.ADDRUN, flag);
+        else route_subprofile<MAXSEG, false>(img, s, PR[1], U.PINF, U.ET, U.IFREZ, SW, BAL, DRIN, DRN[1], PRC[1], U.ADDRUN, flag);
         {
           float EXET = 0.0f;
 #pragma unroll
@@ -1232,7 +1238,8 @@ __global__ void __launch_bounds__(HELP_SIM_THREADS, MINB) help_sim_kernel(SimArg
           const float FINn = (float)(PRC[N - 1] + (double)EXWAT[N]);
           if (N > nprof) break;
           EXWAT[N] = 0.0f;
-          route_subprofile<MAXSEG>(img, s, PR[N], FINn, U.ET, U.IFREZ, SW, BAL, DRIN, DRN[N], PRC[N], EXWAT[N], flag);
+          if (PR[N].subin & 2) route_subprofile<MAXSEG, true>(img, s, PR[N], FINn, U.ET, U.IFREZ, SW, BAL, DRIN, DRN[N], PRC[N], EXWAT[N], flag);
+          else route_subprofile<MAXSEG, false>(img, s, PR[N], FINn, U.ET, U.IFREZ, SW, BAL, DRIN, DRN[N], PRC[N], EXWAT[N], flag);
           if (N <= 5) {
             if (LDn[N] > 0) {
               const double RCR = (double)RECIR[N] * DRN[N] / (double)100.0f;

@@ -35,7 +35,7 @@ extern "C" int emu_run(const help_b200_batch* b, float* monthly, float* yearly, 
   for (int64_t c = 0; c < n; ++c) { blockIdx.x = (unsigned)c; help_setup_kernel(B, img, nullptr, flags, topo, nullptr); }
   SimArgs A; A.img = img; A.pre = pre.data(); A.tmp = tmp.data(); A.rad = rad.data(); A.years = b->years; A.n_years = ny; A.n_cells = n; A.perm = nullptr;
   A.monthly = monthly; A.yearly = yearly; A.raw = raw; A.flags = flags;
-  for (int64_t c = 0; c < n; ++c) { blockIdx.x = (unsigned)c; help_sim_kernel<67>(A); }
+  for (int64_t c = 0; c < n; ++c) { blockIdx.x = (unsigned)c; help_sim_kernel<67, 4>(A); }
   return 0;
 }
 #ifdef HELP_EMU_COUNT
