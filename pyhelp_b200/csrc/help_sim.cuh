@@ -295,7 +295,9 @@ __device__ __noinline__ void route_subprofile(const Image& img, int64_t s, const
         A1 = rec_f4<RV_A>(p1); B1 = rec_f4<RV_B>(p1); C1 = rec_d2<RV_C>(p1); D1 = rec_d2<RV_D>(p1);
         sw1 = SWa(J + 1); bal1 = BALa(J + 1);
       }
+#ifndef HELP_LAZY_E
       const double2 Ev = rec_d2<RV_E>(p);                 // {B of the Newton solve, LOW at WP}
+#endif
       const double ul = (double)A.x, rs = (double)A.y, wp = (double)A.z, fc = (double)A.w;
       const double rspan = Cv.x, kdt = Cv.y;
       const double span = ul - rs;
@@ -333,7 +335,11 @@ __device__ __noinline__ void route_subprofile(const Image& img, int64_t s, const
         swl = (double)SWLIM;
         LOW = kdt * r8_pow(fdiv_by(swl - rs, span, rspan), Dv.x);
       }
+#ifndef HELP_LAZY_E
       else if (kind == 1) { swl = wp; LOW = Ev.y; }
+#else
+      else if (kind == 1) { swl = wp; LOW = rec_d2<RV_E>(p).y; }
+#endif
       else if (kind == 2) { swl = fc; LOW = LOWFC_L; }
       else { swl = ul; LOW = kdt; }            // ((ul - rs)/(ul - rs))**C == 1
       const double base = swj + (balj / 2.0);                     // storage at the start of the step
@@ -397,7 +403,11 @@ __device__ __noinline__ void route_subprofile(const Image& img, int64_t s, const
             // constant of the segment (set-up kernel).  x^C and x^(C-1) share one logarithm.
             double An = PLAIN ? (2.0 * (swj - rs) + balj + drin - Ej) : (2.0 * (swj - rs) + balj + drin + DSUBj - Ej);
             if (add_sub) An = An + (2.0 * DSUBE);
+#ifndef HELP_LAZY_E
             const double Bc = Ev.x;
+#else
+            const double Bc = rec_d2<RV_E>(p).x;
+#endif
             const double TOLER = 0.003 * span;
             const double ftol = (double)0.3f * TOLER;
             const double Cm1 = C - 1.0;
