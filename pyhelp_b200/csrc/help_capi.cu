@@ -263,16 +263,7 @@ static int pick_minb(int64_t n, int device) {
 template <int MAXSEG, int MINB>
 static void launch_sim(const SimArgs& A, int64_t n, cudaStream_t st) {
   const int th = HELP_SIM_THREADS;
-#ifdef HELP_SIM_STATE_SMEM
-#ifdef HELP_SIM_DRIN_SMEM
-  const size_t smem = (size_t)th * (2 * (MAXSEG + 2) + MAXSEG + 3) * sizeof(double);
-#else
-  const size_t smem = (size_t)2 * th * (MAXSEG + 2) * sizeof(double);
-#endif
-  cudaFuncSetAttribute(help_sim_kernel<MAXSEG, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-#else
   const size_t smem = 0;
-#endif
   help_sim_kernel<MAXSEG, MINB><<<(unsigned)((n + th - 1) / th), th, smem, st>>>(A);
 }
 

@@ -213,18 +213,9 @@ struct ProfC {
   FmlC fml;
 };
 
-#ifdef HELP_SIM_STATE_SMEM
-#define HELP_SST ((int)blockDim.x)   // element stride of SW/BAL: [segment][thread] in shared memory
-#else
-#define HELP_SST 1                   // thread-local arrays
-#endif
-#define SWa(j) SW[(j) * HELP_SST]
-#define BALa(j) BAL[(j) * HELP_SST]
-#ifdef HELP_SIM_DRIN_SMEM
-#define DRINa(j) DRIN[(j) * HELP_SST]
-#else
+#define SWa(j) SW[(j)]
+#define BALa(j) BAL[(j)]
 #define DRINa(j) DRIN[(j)]
-#endif
 
 // PLAIN = the subprofile has no liner (IBAR = 0), no subsurface inflow and no lateral-drain
 // layer below it (every natural-soil profile of a PyHELP grid): the liner, lateral-drainage
@@ -612,21 +603,10 @@ __global__ void __launch_bounds__(HELP_SIM_THREADS, MINB) help_sim_kernel(SimArg
     }
   }
   // ---- state (run_simulation F:200-317; READIN F:1344-1351; INITIA F:2437-2442) ---------------
-  // Segment state.  HELP_SIM_STATE_SMEM keeps SW/BAL in shared memory, [segment][thread]
-  // (stride blockDim.x, conflict-free 64-bit accesses), where the streaming of the routing
-  // records through L1 cannot evict it; otherwise the arrays are thread-local (L1-cached).
-#ifdef HELP_SIM_STATE_SMEM
-  extern __shared__ double state_smem[];
-  double* SW = state_smem + threadIdx.x;
-  double* BAL = state_smem + (size_t)(MAXSEG + 2) * blockDim.x + threadIdx.x;
-#ifdef HELP_SIM_DRIN_SMEM
-  double* DRIN = state_smem + (size_t)2 * (MAXSEG + 2) * blockDim.x + threadIdx.x;
-#else
-  double DRIN[MAXSEG + 3];
-#endif
-#else
+  // Segment state: thread-local arrays (L1-cached).  Keeping them in shared memory instead was
+  // measured slower on B200: the carve-out shrinks the L1 the routing records stream through
+  // (profiles/r1_notes.md).
   double SW[MAXSEG + 2], BAL[MAXSEG + 2], DRIN[MAXSEG + 3];
-#endif
   for (int J = 1; J <= NSEG; ++J) { SWa(J) = (double)img.SF(S_SW0, J, s); BALa(J) = 0.0; }
   SWa(0) = 0.0; BALa(0) = 0.0; SWa(NSEG + 1) = 0.0; BALa(NSEG + 1) = 0.0;
   Surf U;
