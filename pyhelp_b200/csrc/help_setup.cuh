@@ -720,15 +720,18 @@ help_setup_kernel(BatchDev B, Image img, const int32_t* __restrict__ perm, uint3
     topo[13 * n + c] = IDFS; topo[14 * n + c] = T.LP[1]; topo[15 * n + c] = T.LD[1];
   }
   if (sortkey) {
-    // class = (subprofile structure, step counts); cost-major so the launch is balanced,
-    // weather node minor so neighbouring threads share weather rows and branches
+    // Warps should be uniform in (1) code path: the liner structure of the profile (IBAR of every
+    // subprofile), (2) trip counts: cost = sum of segments x sub-steps, (3) weather: the node,
+    // which decides rain, snow and frozen-soil days for all lanes at once, (4) soil: conductivity
+    // of the top segment.  Most significant first (measured orders: profiles/r1_notes.md).
     uint64_t cost = 0, cls = 0;
     for (int N = 1; N <= 6; ++N) {
       cost += (uint64_t)S.NSEGn[N] * (uint64_t)T.NSTEP[N];
-      cls = cls * 131u + (uint64_t)(S.NSEGn[N] * 8 + img.PI(Q_IBAR, N, slot));
+      cls = cls * 7u + (uint64_t)(S.NSEGn[N] > 0 ? 1 + img.PI(Q_IBAR, N, slot) : 0);
     }
     if (cost > 0xFFFFull) cost = 0xFFFFull;
-    sortkey[slot] = (cost << 48) | ((cls & 0xFFFFFFull) << 24) | ((uint64_t)node_t & 0xFFFFFFull);
+    const uint64_t soil = ((uint64_t)(uint32_t)__float_as_int(S.RCUL[1]) >> 21) & 0x3FFull;
+    sortkey[slot] = ((cls & 0xFFFFull) << 48) | (cost << 32) | (((uint64_t)node_t & 0x3FFFFFull) << 10) | soil;
   }
 }
 
