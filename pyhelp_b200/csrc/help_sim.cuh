@@ -673,7 +673,10 @@ __global__ void __launch_bounds__(HELP_SIM_THREADS, MINB) help_sim_kernel(SimArg
       const float* __restrict__ yrad = wrad + (int64_t)iy * kDays;
       for (int IDA = 1; IDA <= ND; ++IDA) {               // DO 1100
 #ifdef HELP_SIM_DAYSYNC
-        __syncthreads();      // keep the block's warps in the same code region (instruction cache)
+#ifndef HELP_SIM_SYNC_MASK
+#define HELP_SIM_SYNC_MASK 0
+#endif
+        if ((IDA & HELP_SIM_SYNC_MASK) == 0) __syncthreads();      // keep the block's warps in the same code region (instruction cache)
 #endif
         const float PRE = __ldg(ypre + IDA - 1), TMPF = __ldg(ytmp + IDA - 1), RAD = __ldg(yrad + IDA - 1);
         const float RH = RHq[(IDA <= 91) ? 0 : (IDA <= 182) ? 1 : (IDA <= 274) ? 2 : 3];
