@@ -170,11 +170,21 @@ double help_b200_algorithmic_bytes(const help_b200_batch* batch);
 
 /* diagnostic: evaluate on the device the transcendental function `fn` the engine uses
  * (pyhelp_b200/csrc/help_math.h; 0 pow(x,y) 1 exp 2 log 3 sin 4 cos 5 atan, 6..17 the REAL*4
- * wrappers acos tan pow exp log sin cos log10 sqrt x**8 x**7 x**4, 18 the dual-issue pow)
+ * wrappers acos tan pow exp log sin cos log10 sqrt x**8 x**7 x**4, 18 the dual-issue pow,
+ * 19 the shared-logarithm pow pair, 20 x/y through the rounded reciprocal of y)
  * for n host values.  The
  * reference's `**`, EXP, ALOG ... resolve to libm (HELP3O.FOR:1307-1340, 4329-4480); this lets
  * a test prove the device functions return the same bits as the CPU oracle's.               */
 int help_b200_math_eval(int fn, const double* x, const double* y, double* out, int64_t n);
+
+/* ---- adjacent to the path -----------------------------------------
+ * Nearest weather-grid node of every cell: replaces the per-cell loop of
+ * HelpManager._generate_d4d7d13_input_files (reference pyhelp/managers.py:307-313), i.e.
+ * argmin over nodes of calc_dist_from_coord (haversine, r = 6373 km, pyhelp/utils.py:81-96),
+ * first minimum wins.  Degrees in, host pointers; out_index[n_cells] receives node indices.  */
+int help_b200_nearest_nodes(int64_t n_cells, const double* cell_lat, const double* cell_lon,
+                            int32_t n_nodes, const double* node_lat, const double* node_lon,
+                            int32_t* out_index);
 
 #ifdef __cplusplus
 }

@@ -2337,8 +2337,8 @@ extern "C" int help_oracle_math_eval(int fn, const double* x, const double* y, d
       case 16: r = R4_POW7(af); break;
       case 17: r = R4_POW4(af); break;
 #ifndef HELP_ORACLE_GLIBC
-      case 18: { double r0, r1; helpmath::det_pow2(a, b, b == 0.0 ? 1.5 : 1.0 / b, a, r0, r1); r = r0; break; }   // dual-issue form
-      case 19: { double r0, r1; helpmath::det_pow_samebase(a, b - 1.0, b, r0, r1); r = r1; break; }                // shared-logarithm form
+      case 18: { r = helpmath::det_pow2(a, b, b == 0.0 ? 1.5 : 1.0 / b, a).a; break; }   // dual-issue form
+      case 19: { r = helpmath::det_pow_samebase(a, b - 1.0, b).b; break; }                // shared-logarithm form
       case 20: { const double q = a / b; r = helpmath::div_by_const(a, b, 1.0 / b); if (q != q) r = q; break; }     // a/b through RN(1/b)
 #endif
       default: return -1;

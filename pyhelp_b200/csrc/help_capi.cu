@@ -22,6 +22,7 @@
 #include "help_image.h"
 #include "help_setup.cuh"
 #include "help_sim.cuh"
+#include "help_nodes.cuh"
 
 using namespace helpb200;
 
@@ -389,8 +390,8 @@ __global__ void math_eval_kernel(int fn, const double* __restrict__ x, const dou
     case 15: r = r4_pow8(af); break;
     case 16: r = r4_pow7(af); break;
     case 17: r = r4_pow4(af); break;
-    case 18: { double r0, r1; helpmath::det_pow2(a, b, b == 0.0 ? 1.5 : 1.0 / b, a, r0, r1); r = r0; break; }
-    case 19: { double r0, r1; helpmath::det_pow_samebase(a, b - 1.0, b, r0, r1); r = r1; break; }
+    case 18: { r = helpmath::det_pow2(a, b, b == 0.0 ? 1.5 : 1.0 / b, a).a; break; }
+    case 19: { r = helpmath::det_pow_samebase(a, b - 1.0, b).b; break; }
     case 20: { const double q = a / b; r = helpmath::div_by_const(a, b, 1.0 / b); if (q != q) r = q; break; }
     default: break;
   }
@@ -413,6 +414,36 @@ extern "C" int help_b200_math_eval(int fn, const double* x, const double* y, dou
   }
   if (ce == cudaSuccess) ce = cudaMemcpy(out, d_out, sizeof(double) * n, cudaMemcpyDeviceToHost);
   if (ce != cudaSuccess) return done(fail(HELP_B200_ECUDA, "math_eval", ce));
+  return done(0);
+}
+
+extern "C" int help_b200_nearest_nodes(int64_t n_cells, const double* cell_lat, const double* cell_lon, int32_t n_nodes,
+                                       const double* node_lat, const double* node_lon, int32_t* out_index) {
+  if (n_cells < 0 || n_nodes < 1 || !node_lat || !node_lon || (n_cells > 0 && (!cell_lat || !cell_lon || !out_index)))
+    return fail(HELP_B200_EINVAL, "nearest_nodes: bad argument");
+  if (help_b200_device_count() < 1) return fail(HELP_B200_ENODEV, "no CUDA device (this engine has no CPU path)");
+  if (n_cells == 0) return 0;
+  double *d_clat = nullptr, *d_clon = nullptr, *d_nlat = nullptr, *d_nlon = nullptr;
+  NodeVec* d_vec = nullptr; int32_t* d_out = nullptr;
+  int rc = 0;
+  auto done = [&](int code) {
+    for (void* p : {(void*)d_clat, (void*)d_clon, (void*)d_nlat, (void*)d_nlon, (void*)d_vec, (void*)d_out}) if (p) cudaFree(p);
+    return code;
+  };
+  if ((rc = dev_alloc(&d_clat, (size_t)n_cells)) || (rc = dev_alloc(&d_clon, (size_t)n_cells)) || (rc = dev_alloc(&d_nlat, (size_t)n_nodes)) ||
+      (rc = dev_alloc(&d_nlon, (size_t)n_nodes)) || (rc = dev_alloc(&d_vec, (size_t)n_nodes)) || (rc = dev_alloc(&d_out, (size_t)n_cells)))
+    return done(rc);
+  cudaError_t ce = cudaMemcpy(d_clat, cell_lat, sizeof(double) * n_cells, cudaMemcpyHostToDevice);
+  if (ce == cudaSuccess) ce = cudaMemcpy(d_clon, cell_lon, sizeof(double) * n_cells, cudaMemcpyHostToDevice);
+  if (ce == cudaSuccess) ce = cudaMemcpy(d_nlat, node_lat, sizeof(double) * n_nodes, cudaMemcpyHostToDevice);
+  if (ce == cudaSuccess) ce = cudaMemcpy(d_nlon, node_lon, sizeof(double) * n_nodes, cudaMemcpyHostToDevice);
+  if (ce == cudaSuccess) {
+    node_vectors_kernel<<<(unsigned)((n_nodes + 255) / 256), 256>>>(d_nlat, d_nlon, n_nodes, d_vec);
+    nearest_node_kernel<<<(unsigned)((n_cells + 255) / 256), 256>>>(d_clat, d_clon, n_cells, d_vec, n_nodes, d_out);
+    ce = cudaGetLastError();
+  }
+  if (ce == cudaSuccess) ce = cudaMemcpy(out_index, d_out, sizeof(int32_t) * n_cells, cudaMemcpyDeviceToHost);
+  if (ce != cudaSuccess) return done(fail(HELP_B200_ECUDA, "nearest_nodes", ce));
   return done(0);
 }
 

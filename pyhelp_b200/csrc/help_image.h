@@ -198,10 +198,12 @@ using helpmath::r4_cos; using helpmath::r4_tan; using helpmath::r4_acos; using h
 using helpmath::r4_sqrt; using helpmath::r4_pow8; using helpmath::r4_pow7; using helpmath::r4_pow4;
 __host__ __device__ __forceinline__ double r8_pow(double x, double y) { return helpmath::det_pow(x, y); }
 __host__ __device__ __forceinline__ void r8_pow2(double x0, double y0, double x1, double y1, double& r0, double& r1) {
-  helpmath::det_pow2(x0, y0, x1, y1, r0, r1);   // two independent powers, same bits as r8_pow
+  const helpmath::Pair R = helpmath::det_pow2(x0, y0, x1, y1);   // two independent powers, same bits as r8_pow
+  r0 = R.a; r1 = R.b;
 }
 __host__ __device__ __forceinline__ void r8_pow_sb(double x, double y0, double y1, double& r0, double& r1) {
-  helpmath::det_pow_samebase(x, y0, y1, r0, r1);   // x**y0 and x**y1, same bits as two r8_pow calls
+  const helpmath::Pair R = helpmath::det_pow_samebase(x, y0, y1);   // x**y0 and x**y1, same bits as two r8_pow calls
+  r0 = R.a; r1 = R.b;
 }
 __host__ __device__ __forceinline__ double r8_log(double x) { return helpmath::det_log(x); }
 __host__ __device__ __forceinline__ double r8_atan(double x) { return helpmath::det_atan(x); }

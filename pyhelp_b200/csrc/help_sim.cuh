@@ -213,20 +213,29 @@ struct ProfC {
   FmlC fml;
 };
 
-#define SWa(j) SW[(j)]
-#define BALa(j) BAL[(j)]
-#define DRINa(j) DRIN[(j)]
+// Per-cell segment state, one object so that the routing function addresses all of it from one
+// pointer: SB[j] = {SW, BAL} of segment j (always read and written together: one 16-byte
+// access), DRIN[j] = inflow into segment j during the current sub-step.
+template <int MAXSEG>
+struct SegState {
+  double2 SB[MAXSEG + 2];
+  double DRIN[MAXSEG + 3];
+};
+struct RouteOut { double DRN, PRC; float EXTRA; uint32_t flag; };
+#define SWa(j) SS.SB[(j)].x
+#define BALa(j) SS.SB[(j)].y
+#define DRINa(j) SS.DRIN[(j)]
 
 // PLAIN = the subprofile has no liner (IBAR = 0), no subsurface inflow and no lateral-drain
 // layer below it (every natural-soil profile of a PyHELP grid): the liner, lateral-drainage
 // and inflow terms fold away at compile time.  Adding the inflow term 0.0 is the identity
 // there (none of the partial sums can be -0.0), so it is dropped too.
 template <int MAXSEG, bool PLAIN>
-__device__ __noinline__ void route_subprofile(const Image& img, int64_t s, const ProfC& P, float FIN,
-                                              const float* __restrict__ ET7, int IFREZ,
-                                              double* __restrict__ SW, double* __restrict__ BAL,
-                                              double* __restrict__ DRIN, double& DRNo, double& PRCo,
-                                              float& EXTRA, uint32_t& flag) {
+__device__ __noinline__ RouteOut route_subprofile(const Image& img, int64_t s, const ProfC& P, float FIN,
+                                                  const float* __restrict__ ET7, int IFREZ,
+                                                  SegState<MAXSEG>& SS) {
+  uint32_t flag = 0;
+  float EXTRA = 0.0f;
   const int NSEGB = P.NSEGB, NSEGE = P.NSEGE, NSEG = P.NSEG;
   const int IBAR = PLAIN ? 0 : P.ibar, LAT = PLAIN ? 0 : P.lat;
   const int NSEGL = (IBAR == 0 || IBAR == 3) ? NSEGE : NSEGE - 1;
@@ -243,7 +252,6 @@ __device__ __noinline__ void route_subprofile(const Image& img, int64_t s, const
 #pragma unroll
   for (int J = 1; J <= 7; ++J) Ed[J] = (double)ET7[J] * DT;
   double EXCESS = 0.0, PRC = 0.0, DRN = 0.0;
-  EXTRA = 0.0f;
   for (int K = 1; K <= P.nstep; ++K) {
     DRINa(NSEGB) = F + EXCESS;
     EXCESS = 0.0;
@@ -275,7 +283,8 @@ __device__ __noinline__ void route_subprofile(const Image& img, int64_t s, const
     const char* p = p0;
     float4 A = rec_f4<RV_A>(p), B = rec_f4<RV_B>(p);
     double2 Cv = rec_d2<RV_C>(p), Dv = rec_d2<RV_D>(p);
-    double swj = SWa(NSEGB), balj = BALa(NSEGB);
+    double swj, balj;
+    { const double2 sb = SS.SB[NSEGB]; swj = sb.x; balj = sb.y; }
     double drin = DRINa(NSEGB);
     for (int J = NSEGB; J <= NSEGL; ++J, p += kRecBytes) {
       float4 A1 = A, B1 = B;
@@ -284,7 +293,7 @@ __device__ __noinline__ void route_subprofile(const Image& img, int64_t s, const
       if (J < NSEGL) {
         const char* p1 = p + kRecBytes;
         A1 = rec_f4<RV_A>(p1); B1 = rec_f4<RV_B>(p1); C1 = rec_d2<RV_C>(p1); D1 = rec_d2<RV_D>(p1);
-        sw1 = SWa(J + 1); bal1 = BALa(J + 1);
+        { const double2 sb = SS.SB[J + 1]; sw1 = sb.x; bal1 = sb.y; }
       }
 #ifndef HELP_LAZY_E
       const double2 Ev = rec_d2<RV_E>(p);                 // {B of the Newton solve, LOW at WP}
@@ -404,6 +413,7 @@ __device__ __noinline__ void route_subprofile(const Image& img, int64_t s, const
             const double Cm1 = C - 1.0;
             double X0 = (SWMAX + SWMIN) / 2.0;
             int ITER;
+#pragma unroll 1
             for (ITER = 1; ITER <= 100; ++ITER) {
               double pc, pc1;
               r8_pow_sb(X0, C, Cm1, pc, pc1);
@@ -457,7 +467,8 @@ __device__ __noinline__ void route_subprofile(const Image& img, int64_t s, const
     {
       const char* pk = pL;
       double dnext = DRINa(NSEGL + 1);
-      double din = DRINa(NSEGL), swk = SWa(NSEGL), balk = BALa(NSEGL);
+      double din = DRINa(NSEGL), swk, balk;
+      { const double2 sb = SS.SB[NSEGL]; swk = sb.x; balk = sb.y; }
       float ulf = rec_f4<RV_A>(pk).x;
       for (int Kk = NSEGL; Kk >= NSEGB; --Kk) {
         const double sub = has_sub ? (double)rec_tail(pk).subin * DT : 0.0;
@@ -465,7 +476,8 @@ __device__ __noinline__ void route_subprofile(const Image& img, int64_t s, const
         float ulf_n = 0.0f;
         if (Kk > NSEGB) {                        // the loads of the next segment up, ahead of their use
           pk -= kRecBytes;
-          din_n = DRINa(Kk - 1); swk_n = SWa(Kk - 1); balk_n = BALa(Kk - 1); ulf_n = rec_f4<RV_A>(pk).x;
+          din_n = DRINa(Kk - 1); ulf_n = rec_f4<RV_A>(pk).x;
+          { const double2 sb = SS.SB[Kk - 1]; swk_n = sb.x; balk_n = sb.y; }
         }
         const double ul = (double)ulf;
         const double Ek = (Kk <= 7) ? Ed[Kk] : 0.0;
@@ -485,8 +497,7 @@ __device__ __noinline__ void route_subprofile(const Image& img, int64_t s, const
           BALT = BALT + EXCE;
           newsw = swk + ((balk + BALT) / 2.0);
         }
-        SWa(Kk) = newsw;
-        BALa(Kk) = BALT;
+        SS.SB[Kk] = make_double2(newsw, BALT);
         dnext = din; din = din_n; swk = swk_n; balk = balk_n; ulf = ulf_n;
       }
     }
@@ -495,8 +506,9 @@ __device__ __noinline__ void route_subprofile(const Image& img, int64_t s, const
     PRC = PRC + prc_step;
     DRN = liner ? (DRN + drn_step) : 0.0;
   }
-  DRNo = DRN;
-  PRCo = PRC;
+  RouteOut R;
+  R.DRN = DRN; R.PRC = PRC; R.EXTRA = EXTRA; R.flag = flag;
+  return R;
 }
 
 // ---- evapotranspiration demand over the 7 evaporative segments (ETCHK/WFS) --------------
@@ -606,7 +618,7 @@ __global__ void __launch_bounds__(HELP_SIM_THREADS, MINB) help_sim_kernel(SimArg
   // Segment state: thread-local arrays (L1-cached).  Keeping them in shared memory instead was
   // measured slower on B200: the carve-out shrinks the L1 the routing records stream through
   // (profiles/r1_notes.md).
-  double SW[MAXSEG + 2], BAL[MAXSEG + 2], DRIN[MAXSEG + 3];
+  SegState<MAXSEG> SS;
   for (int J = 1; J <= NSEG; ++J) { SWa(J) = (double)img.SF(S_SW0, J, s); BALa(J) = 0.0; }
   SWa(0) = 0.0; BALa(0) = 0.0; SWa(NSEG + 1) = 0.0; BALa(NSEG + 1) = 0.0;
   Surf U;
@@ -1197,8 +1209,11 @@ __global__ void __launch_bounds__(HELP_SIM_THREADS, MINB) help_sim_kernel(SimArg
 #ifdef HELP_DBG_PRE
         HELP_DBG_PRE
 #endif
-        if (PR[1].subin & 2) route_subprofile<MAXSEG, true>(img, s, PR[1], U.PINF, U.ET, U.IFREZ, SW, BAL, DRIN, DRN[1], PRC[1], U.ADDRUN, flag);
-        else route_subprofile<MAXSEG, false>(img, s, PR[1], U.PINF, U.ET, U.IFREZ, SW, BAL, DRIN, DRN[1], PRC[1], U.ADDRUN, flag);
+        {
+          const RouteOut R = (PR[1].subin & 2) ? route_subprofile<MAXSEG, true>(img, s, PR[1], U.PINF, U.ET, U.IFREZ, SS)
+                                               : route_subprofile<MAXSEG, false>(img, s, PR[1], U.PINF, U.ET, U.IFREZ, SS);
+          DRN[1] = R.DRN; PRC[1] = R.PRC; U.ADDRUN = R.EXTRA; flag |= R.flag;
+        }
         {
           float EXET = 0.0f;
 #pragma unroll
@@ -1231,8 +1246,11 @@ __global__ void __launch_bounds__(HELP_SIM_THREADS, MINB) help_sim_kernel(SimArg
           const float FINn = (float)(PRC[N - 1] + (double)EXWAT[N]);
           if (N > nprof) break;
           EXWAT[N] = 0.0f;
-          if (PR[N].subin & 2) route_subprofile<MAXSEG, true>(img, s, PR[N], FINn, U.ET, U.IFREZ, SW, BAL, DRIN, DRN[N], PRC[N], EXWAT[N], flag);
-          else route_subprofile<MAXSEG, false>(img, s, PR[N], FINn, U.ET, U.IFREZ, SW, BAL, DRIN, DRN[N], PRC[N], EXWAT[N], flag);
+          {
+            const RouteOut R = (PR[N].subin & 2) ? route_subprofile<MAXSEG, true>(img, s, PR[N], FINn, U.ET, U.IFREZ, SS)
+                                                 : route_subprofile<MAXSEG, false>(img, s, PR[N], FINn, U.ET, U.IFREZ, SS);
+            DRN[N] = R.DRN; PRC[N] = R.PRC; EXWAT[N] = R.EXTRA; flag |= R.flag;
+          }
           if (N <= 5) {
             if (LDn[N] > 0) {
               const double RCR = (double)RECIR[N] * DRN[N] / (double)100.0f;

@@ -74,8 +74,10 @@ static inline double r8_sqrt(double x) { return helpmath::hm_sqrt(x); }
 static long long g_cap[8]; static float g_prev_relsw[128];
 #define HELP_DBG_CAP { g_cap[0]++; if (RELSW == RELMIN) g_cap[1]++; if ((double)PSIJP1 == c.bub) g_cap[2]++; if ((double)SWLIM == c.wp) g_cap[3]++; if ((double)SWLIM == c.fc) g_cap[4]++; if (RELSW == g_prev_relsw[J]) g_cap[5]++; g_prev_relsw[J] = RELSW; }
 #define r8_pow(x, y) (g_pow_count[__LINE__ & 4095]++, helpmath::det_pow(x, y))
-#define r8_pow2(x0, y0, x1, y1, r0, r1) (g_pow_count[__LINE__ & 4095] += 2, helpmath::det_pow2(x0, y0, x1, y1, r0, r1))
-#define r8_pow_sb(x, y0, y1, r0, r1) (g_pow_count[__LINE__ & 4095] += 2, helpmath::det_pow_samebase(x, y0, y1, r0, r1))
+static inline void emu_pow2(double x0, double y0, double x1, double y1, double& r0, double& r1) { auto R = helpmath::det_pow2(x0, y0, x1, y1); r0 = R.a; r1 = R.b; }
+static inline void emu_pow_sb(double x, double y0, double y1, double& r0, double& r1) { auto R = helpmath::det_pow_samebase(x, y0, y1); r0 = R.a; r1 = R.b; }
+#define r8_pow2(x0, y0, x1, y1, r0, r1) (g_pow_count[__LINE__ & 4095] += 2, emu_pow2(x0, y0, x1, y1, r0, r1))
+#define r8_pow_sb(x, y0, y1, r0, r1) (g_pow_count[__LINE__ & 4095] += 2, emu_pow_sb(x, y0, y1, r0, r1))
 #endif
 
 #ifdef HELP_EMU_MEMO   // per-cell event streams: would a memo of the previous evaluation have hit?

@@ -5,7 +5,7 @@
 static int g_dbg_cell = -1; static int g_ipre=0, g_ida=0;
 #define HELP_DBG_PRE g_ipre=IPRE; g_ida=IDA;
 #define HELP_DBG_SEG if ((int)s==g_dbg_cell && g_ipre==0 && g_ida==150) printf("S J %d swlim %.9g drnmax %.17g out %.17g base %.17g\n", J, SWLIM, DRNMAX, out, base);
-#define HELP_DBG_DAY if ((int)s == g_dbg_cell) { printf("D ipre %d day %d pinf %.9g ett %.9g es %.9g ep %.9g run %.9g addrun %.9g ifrez %d ET:", IPRE, IDA, U.PINF, U.ETT, U.ES, U.EP, U.RUN, U.ADDRUN, U.IFREZ); for (int J = 1; J <= 7; ++J) printf(" %.9g", U.ET[J]); printf(" SW:"); for (int J = 1; J <= NSEG; ++J) printf(" %.17g", SW[J]); printf(" BAL:"); for (int J = 1; J <= NSEG; ++J) printf(" %.17g", BAL[J]);printf("\n"); }
+#define HELP_DBG_DAY if ((int)s == g_dbg_cell) { printf("D ipre %d day %d pinf %.9g ett %.9g es %.9g ep %.9g run %.9g addrun %.9g ifrez %d ET:", IPRE, IDA, U.PINF, U.ETT, U.ES, U.EP, U.RUN, U.ADDRUN, U.IFREZ); for (int J = 1; J <= 7; ++J) printf(" %.9g", U.ET[J]); printf(" SW:"); for (int J = 1; J <= NSEG; ++J) printf(" %.17g", SWa(J)); printf(" BAL:"); for (int J = 1; J <= NSEG; ++J) printf(" %.17g", BALa(J));printf("\n"); }
 #include <cstdio>
 #include <vector>
 #include "../../include/help_b200.h"
