@@ -186,6 +186,22 @@ int help_b200_nearest_nodes(int64_t n_cells, const double* cell_lat, const doubl
                             int32_t n_nodes, const double* node_lat, const double* node_lon,
                             int32_t* out_index);
 
+/* The reductions PyHELP applies to the result, on the engine's device-
+ * resident monthly buffer (engine created with want_monthly, after engine_simulate):
+ *   HelpManager._post_process_output  (reference pyhelp/managers.py:448-506): a cell whose rechg
+ *     holds a NaN is a NaN cell; the recharge of a cell with context == 2 (next to a stream)
+ *     becomes subsurface runoff (subrun1 if its subrun2 is all zero, else subrun2);
+ *   HelpOutput.calc_area_monthly_avg  (pyhelp/output.py:127-152): nansum over cells / Np;
+ *   HelpOutput.calc_cells_yearly_avg  (pyhelp/output.py:171-203): per cell, mean over the years
+ *     with year_from <= year <= year_to of the yearly sums.
+ * context: int32[n_cells] in the caller's cell order, or NULL (no cell next to a stream).
+ * Outputs (host, each may be NULL): area_monthly double[7][n_years][12] (rows HR_*),
+ * cells_yearly double[7][n_cells], nan_mask uint8[n_cells] (1 = NaN cell, the reference's
+ * idx_nan).                                                                               */
+int help_b200_engine_post_process(help_b200_engine* e, const int32_t* context, int32_t year_from,
+                                  int32_t year_to, double* area_monthly, double* cells_yearly,
+                                  uint8_t* nan_mask);
+
 #ifdef __cplusplus
 }
 #endif

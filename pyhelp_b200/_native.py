@@ -95,6 +95,8 @@ def lib():
     L.help_b200_set_device.argtypes = [C.c_int]
     L.help_b200_math_eval.restype = C.c_int
     L.help_b200_math_eval.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
+    L.help_b200_engine_post_process.restype = C.c_int
+    L.help_b200_engine_post_process.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     L.help_b200_nearest_nodes.restype = C.c_int
     L.help_b200_nearest_nodes.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     if L.help_b200_abi_version() != 1:

@@ -23,6 +23,7 @@
 #include "help_setup.cuh"
 #include "help_sim.cuh"
 #include "help_nodes.cuh"
+#include "help_post.cuh"
 
 using namespace helpb200;
 
@@ -359,6 +360,51 @@ extern "C" int help_b200_engine_fetch(help_b200_engine* e, help_b200_result* r) 
   CU(cudaEventElapsedTime(&r->ms_d2h, e->ev[0], e->ev[1]));
   r->ms_h2d = e->ms_h2d; r->ms_setup = e->ms_setup; r->ms_simulate = e->ms_sim; r->n_launches = e->n_launches;
   return 0;
+}
+
+extern "C" int help_b200_engine_post_process(help_b200_engine* e, const int32_t* context, int32_t year_from, int32_t year_to,
+                                             double* area_monthly, double* cells_yearly, uint8_t* nan_mask) {
+  if (!e) return fail(HELP_B200_EINVAL, "engine is NULL");
+  if (!e->d_monthly) return fail(HELP_B200_EINVAL, "post_process needs an engine created with want_monthly");
+  CU(cudaSetDevice(e->device));
+  const int64_t n = e->n; const int ny = e->ny;
+  if (n == 0) return 0;
+  std::vector<int32_t> years(ny);
+  CU(cudaMemcpy(years.data(), e->d_years, sizeof(int32_t) * ny, cudaMemcpyDeviceToHost));
+  int y0 = ny, y1 = 0;                                   // selected years are a contiguous range (years ascend)
+  for (int y = 0; y < ny; ++y) if (years[y] >= year_from && years[y] <= year_to) { if (y < y0) y0 = y; y1 = y + 1; }
+  if (y1 < y0) y1 = y0;
+  int32_t* d_ctx = nullptr; int8_t* d_mode = nullptr; double *d_cy = nullptr, *d_area = nullptr; int32_t* d_nnan = nullptr;
+  int rc = 0;
+  auto done = [&](int code) {
+    for (void* p : {(void*)d_ctx, (void*)d_mode, (void*)d_cy, (void*)d_area, (void*)d_nnan}) if (p) cudaFree(p);
+    return code;
+  };
+  if ((rc = dev_alloc(&d_mode, (size_t)n)) || (rc = dev_alloc(&d_area, (size_t)7 * ny * 12)) || (rc = dev_alloc(&d_nnan, 1)) ||
+      (context && (rc = dev_alloc(&d_ctx, (size_t)n))) || (cells_yearly && (rc = dev_alloc(&d_cy, (size_t)7 * n))))
+    return done(rc);
+  cudaError_t ce = cudaSuccess;
+  if (context) ce = cudaMemcpy(d_ctx, context, sizeof(int32_t) * n, cudaMemcpyHostToDevice);
+  if (ce == cudaSuccess) {
+    post_cell_kernel<<<(unsigned)((n + 127) / 128), 128>>>(e->d_monthly, d_ctx, n, ny, y0, y1, d_mode, d_cy);
+    post_area_kernel<<<(unsigned)(ny * 12), 256>>>(e->d_monthly, d_mode, n, ny, d_area, d_nnan);
+    ce = cudaGetLastError();
+  }
+  int32_t n_nan = 0;
+  if (ce == cudaSuccess) ce = cudaMemcpy(&n_nan, d_nnan, sizeof(int32_t), cudaMemcpyDeviceToHost);
+  if (ce == cudaSuccess && area_monthly) {
+    ce = cudaMemcpy(area_monthly, d_area, sizeof(double) * 7 * ny * 12, cudaMemcpyDeviceToHost);
+    const double np_valid = (double)(n - n_nan);         // Np = cells - NaN cells (output.py:138)
+    if (ce == cudaSuccess) for (int64_t i = 0; i < (int64_t)7 * ny * 12; ++i) area_monthly[i] /= np_valid;
+  }
+  if (ce == cudaSuccess && cells_yearly) ce = cudaMemcpy(cells_yearly, d_cy, sizeof(double) * 7 * n, cudaMemcpyDeviceToHost);
+  if (ce == cudaSuccess && nan_mask) {
+    std::vector<int8_t> m((size_t)n);
+    ce = cudaMemcpy(m.data(), d_mode, (size_t)n, cudaMemcpyDeviceToHost);
+    if (ce == cudaSuccess) for (int64_t i = 0; i < n; ++i) nan_mask[i] = (m[i] == 1);
+  }
+  if (ce != cudaSuccess) return done(fail(HELP_B200_ECUDA, "post_process", ce));
+  return done(0);
 }
 
 extern "C" void help_b200_engine_destroy(help_b200_engine* e) { engine_free(e); }

@@ -326,6 +326,9 @@ __device__ __noinline__ RouteOut route_subprofile(const Image& img, int64_t s, c
         const double base1 = sw1 + (bal1 / 2.0);
         float RELSW = (float)fdiv_by(base1 - rs1, ul1 - rs1, C1.x);
         if (RELSW < B1.z) RELSW = B1.z;
+#ifdef HELP_DBG_CAPMEMO
+        HELP_DBG_CAPMEMO
+#endif
         float PSIJP1 = (float)(bub1 * r8_pow((double)RELSW, D1.y));
         if ((double)PSIJP1 < bub) PSIJP1 = (float)bub;
         const float RELSWL = (float)r8_pow(bub / (double)PSIJP1, lam);

@@ -80,6 +80,30 @@ class HelpEngine:
         out["years"] = b.years.astype(np.uint16)
         return out
 
+    def post_process(self, context=None, year_from=None, year_to=None) -> dict:
+        """PyHELP's result reductions on the device-resident monthly buffer (no 7 x (Np, Ny, 12)
+        float64 arrays on the host): ``HelpManager._post_process_output``
+        (reference ``pyhelp/managers.py:448-506``: NaN cells, context-2 recharge turned into
+        subsurface runoff), ``HelpOutput.calc_area_monthly_avg`` (``pyhelp/output.py:127-152``)
+        and ``HelpOutput.calc_cells_yearly_avg`` (``pyhelp/output.py:171-203``).
+        Returns ``{'years', 'idx_nan', 'area_monthly_avg': {var: [Ny, 12]},
+        'cells_yearly_avg': {var: [Np]}}`` keyed like ``pyhelp.output.VARNAMES``."""
+        b = self.batch
+        n, ny = b.n_cells, b.n_years
+        ctx = None if context is None else np.ascontiguousarray(context, dtype=np.int32).reshape(-1)
+        if ctx is not None and ctx.size != n:
+            raise ValueError("context must have one entry per cell")
+        area = np.empty((N.HR_NROWS, ny, 12), dtype=np.float64)
+        cells = np.empty((N.HR_NROWS, n), dtype=np.float64)
+        mask = np.zeros(n, dtype=np.uint8)
+        yf = -(2 ** 31) if year_from is None or year_from == -np.inf else int(year_from)
+        yt = 2 ** 31 - 1 if year_to is None or year_to == np.inf else int(year_to)
+        N.check(N.lib().help_b200_engine_post_process(self._h, N.ptr(ctx), yf, yt, N.ptr(area), N.ptr(cells), N.ptr(mask)),
+                "engine_post_process")
+        return {"years": b.years.astype(np.uint16), "idx_nan": np.nonzero(mask)[0].tolist(),
+                "area_monthly_avg": {k: area[i] for i, k in enumerate(KEYS)},
+                "cells_yearly_avg": {k: cells[i] for i, k in enumerate(KEYS)}}
+
     def close(self):
         if self._h:
             N.lib().help_b200_engine_destroy(self._h)

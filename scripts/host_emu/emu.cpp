@@ -2,8 +2,13 @@
 // on the CPU, thread by thread.  Build: g++ -O1 -g -ffp-contract=off -shared -fPIC emu.cpp -o libemu.so
 #include "cuda_shim.h"
 #include <cstdio>
+#ifdef HELP_DBG_CAPMEMO
+extern "C" void memo2_newcell();
+#endif
 static int g_dbg_cell = -1; static int g_ipre=0, g_ida=0;
+#ifndef HELP_DBG_PRE
 #define HELP_DBG_PRE g_ipre=IPRE; g_ida=IDA;
+#endif
 #define HELP_DBG_SEG if ((int)s==g_dbg_cell && g_ipre==0 && g_ida==150) printf("S J %d swlim %.9g drnmax %.17g out %.17g base %.17g\n", J, SWLIM, DRNMAX, out, base);
 #define HELP_DBG_DAY if ((int)s == g_dbg_cell) { printf("D ipre %d day %d pinf %.9g ett %.9g es %.9g ep %.9g run %.9g addrun %.9g ifrez %d ET:", IPRE, IDA, U.PINF, U.ETT, U.ES, U.EP, U.RUN, U.ADDRUN, U.IFREZ); for (int J = 1; J <= 7; ++J) printf(" %.9g", U.ET[J]); printf(" SW:"); for (int J = 1; J <= NSEG; ++J) printf(" %.17g", SWa(J)); printf(" BAL:"); for (int J = 1; J <= NSEG; ++J) printf(" %.17g", BALa(J));printf("\n"); }
 #include <cstdio>
@@ -35,7 +40,11 @@ extern "C" int emu_run(const help_b200_batch* b, float* monthly, float* yearly, 
   for (int64_t c = 0; c < n; ++c) { blockIdx.x = (unsigned)c; help_setup_kernel(B, img, nullptr, flags, topo, nullptr); }
   SimArgs A; A.img = img; A.pre = pre.data(); A.tmp = tmp.data(); A.rad = rad.data(); A.years = b->years; A.n_years = ny; A.n_cells = n; A.perm = nullptr;
   A.monthly = monthly; A.yearly = yearly; A.raw = raw; A.flags = flags;
+#ifdef HELP_DBG_CAPMEMO
+  for (int64_t c = 0; c < n; ++c) { blockIdx.x = (unsigned)c; memo2_newcell(); help_sim_kernel<67, 4>(A); }
+#else
   for (int64_t c = 0; c < n; ++c) { blockIdx.x = (unsigned)c; help_sim_kernel<67, 4>(A); }
+#endif
   return 0;
 }
 #ifdef HELP_EMU_COUNT
