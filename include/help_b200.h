@@ -186,6 +186,18 @@ int help_b200_nearest_nodes(int64_t n_cells, const double* cell_lat, const doubl
                             int32_t n_nodes, const double* node_lat, const double* node_lon,
                             int32_t* out_index);
 
+/* Daily channel: the reference's daily output (IOD = 1: OUTDAY,
+ * HELP3O.FOR:5984-6029, parsed by read_daily_help_output, pyhelp/processing.py:150-220) for a
+ * few selected cells -- a verification channel, not a bulk output.  select_daily() before
+ * engine_simulate(); fetch_daily() afterwards fills out[n_selected][n_days][16] (double, inches,
+ * unrounded; n_days = days of the output years, 365/366 by the MOD-4 rule) with the columns
+ * precipitation, runoff, evapotranspiration, evaporative-zone water content, then head on the
+ * liner / lateral drainage / percolation for subprofiles 1..3, air-temperature freeze flag,
+ * soil-freeze flag, snow water.                                                            */
+#define HELP_B200_DAILY_COLS 16
+int help_b200_engine_select_daily(help_b200_engine* e, const int32_t* cells, int32_t n_selected);
+int help_b200_engine_fetch_daily(help_b200_engine* e, double* out, int64_t* n_days);
+
 /* The reductions PyHELP applies to the result, on the engine's device-
  * resident monthly buffer (engine created with want_monthly, after engine_simulate):
  *   HelpManager._post_process_output  (reference pyhelp/managers.py:448-506): a cell whose rechg

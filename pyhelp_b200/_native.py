@@ -27,6 +27,7 @@ HL_TYPE, HL_ISOIL, HL_LAYR, HL_IPQ, HL_NLAYER_I32 = range(5)
 HR_PRECIP, HR_RUNOFF, HR_EVAPO, HR_SUBRUN1, HR_SUBRUN2, HR_PERCO, HR_RECHG, HR_NROWS = range(8)
 HY_PRECIP, HY_RUNOFF, HY_EVAPO, HY_LATDRAIN, HY_RECHG, HY_NROWS = range(6)
 RAW_ROWS = 14
+DAILY_COLS = 16
 DAYS = 368
 FLAG_NONCONV, FLAG_NAN, FLAG_OVERFLOW, FLAG_RECIRC, FLAG_BADCELL = 0x1, 0x2, 0x4, 0x8, 0x10
 
@@ -95,6 +96,10 @@ def lib():
     L.help_b200_set_device.argtypes = [C.c_int]
     L.help_b200_math_eval.restype = C.c_int
     L.help_b200_math_eval.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
+    L.help_b200_engine_select_daily.restype = C.c_int
+    L.help_b200_engine_select_daily.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
+    L.help_b200_engine_fetch_daily.restype = C.c_int
+    L.help_b200_engine_fetch_daily.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_int64)]
     L.help_b200_engine_post_process.restype = C.c_int
     L.help_b200_engine_post_process.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     L.help_b200_nearest_nodes.restype = C.c_int

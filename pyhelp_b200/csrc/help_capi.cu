@@ -79,6 +79,7 @@ struct help_b200_engine {
   uint32_t* d_flags = nullptr; int32_t* d_topo = nullptr;
   uint64_t *d_key = nullptr, *d_key2 = nullptr; int32_t *d_perm = nullptr, *d_iota = nullptr;
   void* d_cub = nullptr; size_t cub_bytes = 0;
+  double* d_daily = nullptr; int32_t* d_daily_row = nullptr; int32_t n_daily = 0; int64_t daily_days = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   float ms_h2d = 0, ms_setup = 0, ms_sim = 0;
@@ -92,7 +93,7 @@ static void engine_free(help_b200_engine* e) {
   void* ptrs[] = {e->d_years, e->d_pre, e->d_tmp, e->d_rad, e->d_tm, e->d_iu4, e->d_iu7, e->d_iu13, e->d_idfs,
                   e->d_cell_f32, e->d_layer_f32, e->d_cell_i32, e->d_layer_i32, e->d_layer_rc, e->d_img_f32,
                   e->d_img_i32, e->d_img_f64, e->d_img_rec, e->d_monthly, e->d_yearly, e->d_raw, e->d_flags, e->d_topo,
-                  e->d_key, e->d_key2, e->d_perm, e->d_iota, e->d_cub};
+                  e->d_key, e->d_key2, e->d_perm, e->d_iota, e->d_cub, e->d_daily, e->d_daily_row};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (auto& ev : e->ev) if (ev) cudaEventDestroy(ev);
   if (e->stream) cudaStreamDestroy(e->stream);
@@ -293,6 +294,7 @@ extern "C" int help_b200_engine_simulate(help_b200_engine* e, void* stream) {
     A.img = img; A.pre = e->d_pre; A.tmp = e->d_tmp; A.rad = e->d_rad; A.years = e->d_years;
     A.n_years = e->ny; A.n_cells = n; A.perm = perm;
     A.monthly = e->d_monthly; A.yearly = e->d_yearly; A.raw = e->d_raw; A.flags = e->d_flags;
+    A.daily = e->d_daily; A.daily_row = e->d_daily_row; A.daily_days = e->daily_days;
     switch (e->maxseg_t) {
       case 16:
         switch (pick_minb(n, e->device)) {
@@ -359,6 +361,41 @@ extern "C" int help_b200_engine_fetch(help_b200_engine* e, help_b200_result* r) 
   CU(cudaStreamSynchronize(st));
   CU(cudaEventElapsedTime(&r->ms_d2h, e->ev[0], e->ev[1]));
   r->ms_h2d = e->ms_h2d; r->ms_setup = e->ms_setup; r->ms_simulate = e->ms_sim; r->n_launches = e->n_launches;
+  return 0;
+}
+
+extern "C" int help_b200_engine_select_daily(help_b200_engine* e, const int32_t* cells, int32_t n_selected) {
+  if (!e) return fail(HELP_B200_EINVAL, "engine is NULL");
+  if (n_selected < 0 || (n_selected > 0 && !cells)) return fail(HELP_B200_EINVAL, "select_daily: bad argument");
+  CU(cudaSetDevice(e->device));
+  if (e->d_daily) { cudaFree(e->d_daily); e->d_daily = nullptr; }
+  if (e->d_daily_row) { cudaFree(e->d_daily_row); e->d_daily_row = nullptr; }
+  e->n_daily = 0;
+  if (n_selected == 0) return 0;
+  std::vector<int32_t> row((size_t)e->n, -1);
+  for (int32_t k = 0; k < n_selected; ++k) {
+    if (cells[k] < 0 || cells[k] >= e->n) return fail(HELP_B200_EINVAL, "select_daily: cell index out of range");
+    row[cells[k]] = k;
+  }
+  std::vector<int32_t> years(e->ny);
+  CU(cudaMemcpy(years.data(), e->d_years, sizeof(int32_t) * e->ny, cudaMemcpyDeviceToHost));
+  e->daily_days = 0;
+  for (int y = 0; y < e->ny; ++y) e->daily_days += (years[y] % 4 == 0) ? 366 : 365;      // LEAP, F:1048
+  int rc;
+  if ((rc = dev_alloc(&e->d_daily_row, (size_t)e->n)) || (rc = dev_alloc(&e->d_daily, (size_t)n_selected * e->daily_days * kDailyCols))) return rc;
+  CU(cudaMemcpy(e->d_daily_row, row.data(), sizeof(int32_t) * e->n, cudaMemcpyHostToDevice));
+  CU(cudaMemset(e->d_daily, 0, sizeof(double) * (size_t)n_selected * e->daily_days * kDailyCols));
+  e->n_daily = n_selected;
+  return 0;
+}
+
+extern "C" int help_b200_engine_fetch_daily(help_b200_engine* e, double* out, int64_t* n_days) {
+  if (!e) return fail(HELP_B200_EINVAL, "engine is NULL");
+  if (n_days) *n_days = e->daily_days;
+  if (!e->d_daily || e->n_daily == 0) return fail(HELP_B200_EINVAL, "fetch_daily: no cell was selected (select_daily before simulate)");
+  if (!out) return 0;
+  CU(cudaSetDevice(e->device));
+  CU(cudaMemcpy(out, e->d_daily, sizeof(double) * (size_t)e->n_daily * e->daily_days * kDailyCols, cudaMemcpyDeviceToHost));
   return 0;
 }
 

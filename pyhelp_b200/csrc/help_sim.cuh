@@ -34,6 +34,8 @@
 
 namespace helpb200 {
 
+constexpr int kDailyCols = 16;   // pre, run, ett, swe, (hed, drn, prc) x 3 subprofiles, air-freeze, soil-freeze, sno
+
 struct SimArgs {
   Image img;
   const float* pre;       // [node][year][kDays] inches
@@ -47,6 +49,10 @@ struct SimArgs {
   float* yearly;          // [5][ny][n] or NULL
   float* raw;             // [14][ny][12][n] or NULL
   uint32_t* flags;        // [n]
+  // optional daily channel (OUTDAY columns, F:5984-5996) for selected cells
+  double* daily;          // [n_selected][daily_days][kDailyCols] or NULL
+  const int32_t* daily_row;   // [n] caller cell -> row of `daily`, -1 = not selected
+  int64_t daily_days;     // days of the n_years output years
 };
 
 // value an F7.3 field takes after the reference's print + float32 re-parse
@@ -221,7 +227,7 @@ struct SegState {
   double2 SB[MAXSEG + 2];
   double DRIN[MAXSEG + 3];
 };
-struct RouteOut { double DRN, PRC; float EXTRA; uint32_t flag; };
+struct RouteOut { double DRN, PRC, HED; float EXTRA; uint32_t flag; };
 #define SWa(j) SS.SB[(j)].x
 #define BALa(j) SS.SB[(j)].y
 #define DRINa(j) SS.DRIN[(j)]
@@ -251,7 +257,7 @@ __device__ __noinline__ RouteOut route_subprofile(const Image& img, int64_t s, c
   double Ed[8];                                          // E(J) = ET(J) dt of the evaporative segments
 #pragma unroll
   for (int J = 1; J <= 7; ++J) Ed[J] = (double)ET7[J] * DT;
-  double EXCESS = 0.0, PRC = 0.0, DRN = 0.0;
+  double EXCESS = 0.0, PRC = 0.0, DRN = 0.0, HED = 0.0;
   for (int K = 1; K <= P.nstep; ++K) {
     DRINa(NSEGB) = F + EXCESS;
     EXCESS = 0.0;
@@ -270,6 +276,7 @@ __device__ __noinline__ RouteOut route_subprofile(const Image& img, int64_t s, c
         XHEAD = XHEAD - th;
         if ((XHEAD + 0.00005) < 0.0) break;
       }
+      HED = HED + THY * DT;                    // mean head on the liner over the day (F:4253)
       if (THY > 0.0) {
         // (IBAR 4/5 = bottom liner with subsurface inflow: the Fortran computes no leakage, F:4241-4242)
         if (IBAR == 1) QPERCY = (double)P.drculs * (THY + (double)P.dthics) / (double)P.dthics;
@@ -465,7 +472,6 @@ __device__ __noinline__ RouteOut route_subprofile(const Image& img, int64_t s, c
     // water above saturation into the segment above
     if (IBAR == 3) DRINa(NSEGE + 1) = 0.0;
     const double prc_step = DRINa(NSEGE + 1);
-    const double drn_step = liner ? (DRINa(NSEGL + 1) - DRINa(NSEGE + 1) + DSUBE) : 0.0;
     double EXC = 0.0;
     {
       const char* pk = pL;
@@ -507,10 +513,11 @@ __device__ __noinline__ RouteOut route_subprofile(const Image& img, int64_t s, c
     EXCESS = EXC;
     EXTRA = (float)EXCESS;
     PRC = PRC + prc_step;
-    DRN = liner ? (DRN + drn_step) : 0.0;
+    // left to right, as the reference sums it (F:4250): the daily channel exposes the last bit
+    DRN = liner ? (DRN + DRINa(NSEGL + 1) - DRINa(NSEGE + 1) + DSUBE) : 0.0;
   }
   RouteOut R;
-  R.DRN = DRN; R.PRC = PRC; R.EXTRA = EXTRA; R.flag = flag;
+  R.DRN = DRN; R.PRC = PRC; R.HED = HED; R.EXTRA = EXTRA; R.flag = flag;
   return R;
 }
 
@@ -675,6 +682,9 @@ __global__ void __launch_bounds__(HELP_SIM_THREADS, MINB) help_sim_kernel(SimArg
       for (int J = 1; J <= NSEG; ++J) BALa(J) = 0.0;
     }
     const bool report = (IPRE >= 2);
+    const int dsel = (A.daily && report) ? A.daily_row[cell] : -1;
+    int64_t drow = 0;
+    bool it_snow = false;
     const int npass_years = report ? NY : 1;
     for (int iy = 0; iy < npass_years; ++iy) {           // DO 1090
       const int year = A.years[iy];
@@ -717,6 +727,7 @@ __global__ void __launch_bounds__(HELP_SIM_THREADS, MINB) help_sim_kernel(SimArg
           float SFALL = 0.f, CNHSPX = 0.f, CNHS = 0.f, ROS = 0.f, RAINM = 0.f, XMELT = 0.f, GMWLOS = 0.f, GMSLOS = 0.f;
           float RAIN = 0.f, GMRO = 0.f, SMELT = 0.f;
           bool pack = true, gone = false;
+          it_snow = (TA < PXTEMP);
           if (TA < PXTEMP) {
             U.XLIQW = U.XLIQW + U.ADDRUN * 25.4f;
             U.SNO = U.SNO + U.ADDRUN;
@@ -1208,6 +1219,7 @@ __global__ void __launch_bounds__(HELP_SIM_THREADS, MINB) help_sim_kernel(SimArg
         }
         // ---------------- subsurface routing, subprofile 1 (F:631-693) ----------------
         double DRN[7], PRC[7];
+        double HEDd[4] = {0.0, 0.0, 0.0, 0.0}, DRNd[4] = {0.0, 0.0, 0.0, 0.0};   // daily channel only
         U.ADDRUN = 0.0f;
 #ifdef HELP_DBG_PRE
         HELP_DBG_PRE
@@ -1215,7 +1227,7 @@ __global__ void __launch_bounds__(HELP_SIM_THREADS, MINB) help_sim_kernel(SimArg
         {
           const RouteOut R = (PR[1].subin & 2) ? route_subprofile<MAXSEG, true>(img, s, PR[1], U.PINF, U.ET, U.IFREZ, SS)
                                                : route_subprofile<MAXSEG, false>(img, s, PR[1], U.PINF, U.ET, U.IFREZ, SS);
-          DRN[1] = R.DRN; PRC[1] = R.PRC; U.ADDRUN = R.EXTRA; flag |= R.flag;
+          DRN[1] = R.DRN; PRC[1] = R.PRC; U.ADDRUN = R.EXTRA; flag |= R.flag; HEDd[1] = R.HED; DRNd[1] = R.DRN;
         }
         {
           float EXET = 0.0f;
@@ -1242,6 +1254,7 @@ __global__ void __launch_bounds__(HELP_SIM_THREADS, MINB) help_sim_kernel(SimArg
         if (LDn[1] > 0) {
           const double RCR = (double)RECIR[1] * DRN[1] / (double)100.0f;
           DRN[1] = DRN[1] - RCR;
+          DRNd[1] = DRN[1] + RCR;
         }
         DRNM[1] = (float)((double)DRNM[1] + DRN[1]);
         PRCM[1] = (float)((double)PRCM[1] + PRC[1]);
@@ -1253,11 +1266,13 @@ __global__ void __launch_bounds__(HELP_SIM_THREADS, MINB) help_sim_kernel(SimArg
             const RouteOut R = (PR[N].subin & 2) ? route_subprofile<MAXSEG, true>(img, s, PR[N], FINn, U.ET, U.IFREZ, SS)
                                                  : route_subprofile<MAXSEG, false>(img, s, PR[N], FINn, U.ET, U.IFREZ, SS);
             DRN[N] = R.DRN; PRC[N] = R.PRC; EXWAT[N] = R.EXTRA; flag |= R.flag;
+            if (N <= 3) { HEDd[N] = R.HED; DRNd[N] = R.DRN; }
           }
           if (N <= 5) {
             if (LDn[N] > 0) {
               const double RCR = (double)RECIR[N] * DRN[N] / (double)100.0f;
               DRN[N] = DRN[N] - RCR;
+              if (N <= 3) DRNd[N] = DRN[N] + RCR;
             }
             DRNM[N] = (float)((double)DRNM[N] + DRN[N]);
           }
@@ -1266,6 +1281,21 @@ __global__ void __launch_bounds__(HELP_SIM_THREADS, MINB) help_sim_kernel(SimArg
 #ifdef HELP_DBG_DAY
         HELP_DBG_DAY
 #endif
+        // ---------------- daily channel (OUTDAY columns, F:5984-5996; inches) ----------------
+        if (dsel >= 0) {
+          float SWULE = 0.0f;
+          for (int J = 1; J <= 7; ++J) SWULE = (float)((double)SWULE + SWa(J) + BALa(J) / 2.0);      // F:652
+          double* d = A.daily + ((int64_t)dsel * A.daily_days + drow) * kDailyCols;
+          d[0] = (double)PRE; d[1] = (double)U.RUN; d[2] = (double)U.ETT; d[3] = (double)(SWULE / EDEPTH);
+          for (int N = 1; N <= 3; ++N) {
+            const bool on = (N <= nprof);
+            d[4 + 3 * (N - 1)] = on ? HEDd[N] : 0.0;
+            d[5 + 3 * (N - 1)] = on ? DRNd[N] : 0.0;       // before the recirculated share is taken out (DRN + RCR)
+            d[6 + 3 * (N - 1)] = on ? PRC[N] : 0.0;
+          }
+          d[13] = it_snow ? 1.0 : 0.0; d[14] = (double)U.IFREZ; d[15] = (double)U.SNO;
+          ++drow;
+        }
         // ---------------- month end: report (OUTMO2 semantics) ----------------
         if (IDA == mend + ((MO >= 2) ? NT : 0) || IDA == ND) {
           if (report) {

@@ -29,6 +29,8 @@ from . import _native as N
 from .inputs import CellBatch, batch_from_cellparams
 
 KEYS = ("precip", "runoff", "evapo", "subrun1", "subrun2", "perco", "rechg")
+DAILY_COLS = ("pre", "run", "ett", "swe", "hed1", "drn1", "prc1", "hed2", "drn2", "prc2", "hed3", "drn3", "prc3",
+              "air_freeze", "soil_freeze", "sno")
 
 
 class HelpEngine:
@@ -78,6 +80,23 @@ class HelpEngine:
         out["timing_ms"] = {"h2d": r.ms_h2d, "setup": r.ms_setup, "simulate": r.ms_simulate, "d2h": r.ms_d2h}
         out["n_launches"] = r.n_launches
         out["years"] = b.years.astype(np.uint16)
+        return out
+
+    def select_daily(self, cells):
+        """Ask the next :meth:`simulate` to record the reference's daily output columns (OUTDAY,
+        ``HELP3O.FOR:5984-6029``; ``read_daily_help_output``, ``pyhelp/processing.py:150-220``)
+        for these cell indices (a verification channel for a handful of cells)."""
+        idx = np.ascontiguousarray(cells, dtype=np.int32).reshape(-1)
+        N.check(N.lib().help_b200_engine_select_daily(self._h, N.ptr(idx), idx.size), "select_daily")
+        self._n_daily = idx.size
+        return self
+
+    def fetch_daily(self) -> np.ndarray:
+        """float64 [n_selected, n_days, 16] in inches, unrounded; columns ``DAILY_COLS``."""
+        nd = C.c_int64()
+        N.check(N.lib().help_b200_engine_fetch_daily(self._h, None, C.byref(nd)), "fetch_daily")
+        out = np.empty((self._n_daily, nd.value, N.DAILY_COLS), dtype=np.float64)
+        N.check(N.lib().help_b200_engine_fetch_daily(self._h, N.ptr(out), C.byref(nd)), "fetch_daily")
         return out
 
     def post_process(self, context=None, year_from=None, year_to=None) -> dict:

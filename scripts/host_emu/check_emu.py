@@ -15,10 +15,11 @@ def check(tag, cp):
     r = run_emu.emu_run(b)
     names = list(cp.keys()); worst = 0.0; nbad = 0
     for i, nm in enumerate(names):
-        o = oracle.run_simulation(*cp[nm], full=True)
+        o = oracle.run_simulation(*cp[nm], full=True, daily=True)
         d = np.abs(r["raw"][:, :, :, i] - np.transpose(o["monthly_in"], (1, 0, 2))).max()
         par = np.stack([o[k] for k in oracle.KEYS_PARSED])
         same = np.array_equal(r["monthly"][:, :, :, i], par, equal_nan=True)
+        same = same and np.array_equal(r["daily"][i], o["daily"])       # REAL*8 daily columns, bit for bit
         worst = max(worst, d); nbad += (d != 0) or (not same)
     print("%-10s cells %4d  differing cells %d  max raw diff %.3g in" % (tag, len(names), nbad, worst))
     return nbad

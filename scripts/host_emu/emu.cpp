@@ -20,6 +20,8 @@ static int g_dbg_cell = -1; static int g_ipre=0, g_ida=0;
 using namespace helpb200;
 
 extern "C" void emu_debug_cell(int c) { g_dbg_cell = c; }
+static double* g_daily = nullptr; static int64_t g_daily_days = 0;
+extern "C" void emu_set_daily(double* d, long long days) { g_daily = d; g_daily_days = days; }   // all cells, [cell][day][16]
 extern "C" int emu_run(const help_b200_batch* b, float* monthly, float* yearly, float* raw, uint32_t* flags, int32_t* topo) {
   const int64_t n = b->n_cells; const int ny = b->n_years;
   const size_t wrow = (size_t)ny * kDays;
@@ -39,7 +41,8 @@ extern "C" int emu_run(const help_b200_batch* b, float* monthly, float* yearly, 
   Image img{f32.data(), i32.data(), f64.data(), stride, segcap, rec.data()};
   for (int64_t c = 0; c < n; ++c) { blockIdx.x = (unsigned)c; help_setup_kernel(B, img, nullptr, flags, topo, nullptr); }
   SimArgs A; A.img = img; A.pre = pre.data(); A.tmp = tmp.data(); A.rad = rad.data(); A.years = b->years; A.n_years = ny; A.n_cells = n; A.perm = nullptr;
-  A.monthly = monthly; A.yearly = yearly; A.raw = raw; A.flags = flags;
+  A.monthly = monthly; A.yearly = yearly; A.raw = raw; A.flags = flags; std::vector<int32_t> drow(n); for (int64_t c = 0; c < n; ++c) drow[c] = (int32_t)c;
+  A.daily = g_daily; A.daily_row = g_daily ? drow.data() : nullptr; A.daily_days = g_daily_days;
 #ifdef HELP_DBG_CAPMEMO
   for (int64_t c = 0; c < n; ++c) { blockIdx.x = (unsigned)c; memo2_newcell(); help_sim_kernel<67, 4>(A); }
 #else
