@@ -247,27 +247,24 @@ extern "C" int help_b200_engine_create(const help_b200_batch* b, int want_monthl
 #undef CUB_
 }
 
-// Resident blocks per SM for a batch that needs k = ceil(blocks / SMs) of them: the fewest
-// waves the 80-register build (6 blocks) allows, filled evenly, never below the 128-register
-// build (4 blocks).  HELP_B200_MINB overrides (developer A/B runs).
-static int pick_minb(int64_t n, int device) {
-  if (const char* f = getenv("HELP_B200_MINB")) { const int v = atoi(f); if (v >= 4 && v <= 6) return v; }
+// Launch shapes of help_sim_kernel<16, ..> (help_sim.cuh): threads per SM they keep resident.
+static const int kShapeCap[3] = {512, 640, 768};
+// The shape for a batch of n cells: the fewest waves the largest shape allows, filled evenly,
+// with the most registers that still fit.  HELP_B200_SHAPE overrides (developer A/B runs).
+static int pick_shape(int64_t n, int device) {
+  if (const char* f = getenv("HELP_B200_SHAPE")) { const int v = atoi(f); if (v >= 0 && v <= 2) return v; }
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-  const int64_t blocks = (n + HELP_SIM_THREADS - 1) / HELP_SIM_THREADS;
-  const int64_t k = (blocks + sms - 1) / sms;
-  const int64_t waves = (k + 5) / 6;
-  int64_t m = (k + waves - 1) / waves;
-  if (m < 4) m = 4;
-  if (m > 6) m = 6;
-  return (int)m;
+  const int64_t need = (n + sms - 1) / sms;                     // threads per SM
+  const int64_t waves = (need + kShapeCap[2] - 1) / kShapeCap[2];
+  const int64_t per = (need + waves - 1) / (waves > 0 ? waves : 1);
+  for (int k = 0; k < 3; ++k) if (per <= kShapeCap[k]) return k;
+  return 2;
 }
 
-template <int MAXSEG, int MINB>
+template <int MAXSEG, int THREADS, int REGS>
 static void launch_sim(const SimArgs& A, int64_t n, cudaStream_t st) {
-  const int th = HELP_SIM_THREADS;
-  const size_t smem = 0;
-  help_sim_kernel<MAXSEG, MINB><<<(unsigned)((n + th - 1) / th), th, smem, st>>>(A);
+  help_sim_kernel<MAXSEG, THREADS, REGS><<<(unsigned)((n + THREADS - 1) / THREADS), THREADS, 0, st>>>(A);
 }
 
 extern "C" int help_b200_engine_simulate(help_b200_engine* e, void* stream) {
@@ -297,16 +294,16 @@ extern "C" int help_b200_engine_simulate(help_b200_engine* e, void* stream) {
     A.daily = e->d_daily; A.daily_row = e->d_daily_row; A.daily_days = e->daily_days;
     switch (e->maxseg_t) {
       case 16:
-        switch (pick_minb(n, e->device)) {
-          case 6: launch_sim<16, 6>(A, n, st); break;
-          case 5: launch_sim<16, 5>(A, n, st); break;
-          default: launch_sim<16, 4>(A, n, st); break;
+        switch (pick_shape(n, e->device)) {
+          case 0: launch_sim<16, 128, 128>(A, n, st); break;
+          case 1: launch_sim<16, 128, 96>(A, n, st); break;
+          default: launch_sim<16, 128, 80>(A, n, st); break;
         }
         break;
 #ifndef HELP_DEV_FAST_BUILD
-      case 25: launch_sim<25, 4>(A, n, st); break;
-      case 40: launch_sim<40, 4>(A, n, st); break;
-      default: launch_sim<67, 4>(A, n, st); break;
+      case 25: launch_sim<25, 128, 128>(A, n, st); break;
+      case 40: launch_sim<40, 128, 128>(A, n, st); break;
+      default: launch_sim<67, 128, 128>(A, n, st); break;
 #else
       default: return fail(HELP_B200_EINVAL, "developer build: MAXSEG 16 only");
 #endif

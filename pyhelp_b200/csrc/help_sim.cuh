@@ -546,18 +546,15 @@ struct Surf {      // REAL*4 surface-process state of one cell
 // barrier per day (HELP_SIM_DAYSYNC): the routing code is larger than the 32 KB L1.5
 // instruction cache, and warps that run the same region together share its fetches
 // (measured on B200: +12 % throughput, profiles/r1_notes.md).
-// The kernel is compiled for several register budgets (MINB = resident blocks of
-// HELP_SIM_THREADS threads per SM: 4 -> 128 registers, 5 -> 96, 6 -> 80): all cells of a launch
-// take the same time, so the launcher (help_capi.cu pick_minb) chooses the budget that fits
-// the batch into the fewest, evenly filled waves.
-#ifndef HELP_SIM_THREADS
-#define HELP_SIM_THREADS 128
-#endif
+// The kernel is compiled for several launch shapes (THREADS per block, REGS per thread ->
+// resident threads per SM: 128-thread blocks at 128 registers = 512, at 96 = 640, at 80 = 768): all cells of a launch take the same time, so the launcher (help_capi.cu pick_shape)
+// chooses the shape with the most registers that still fits the batch into the fewest,
+// evenly filled waves.
 #ifndef HELP_SIM_NO_DAYSYNC
 #define HELP_SIM_DAYSYNC 1
 #endif
-template <int MAXSEG, int MINB>
-__global__ void __launch_bounds__(HELP_SIM_THREADS, MINB) help_sim_kernel(SimArgs A) {
+template <int MAXSEG, int THREADS, int REGS>
+__global__ void __launch_bounds__(THREADS) __maxnreg__(REGS) help_sim_kernel(SimArgs A) {
   const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= A.n_cells) return;
   const Image& img = A.img;

@@ -14,6 +14,7 @@
 #define __restrict__
 #define __constant__ static const
 #define __launch_bounds__(...)
+#define __maxnreg__(...)
 struct dim3s { unsigned x, y, z; };
 static thread_local dim3s blockIdx{0, 0, 0}, threadIdx{0, 0, 0}, blockDim{1, 1, 1}, gridDim{1, 1, 1};
 template <typename T> static inline T __ldg(const T* p) { return *p; }

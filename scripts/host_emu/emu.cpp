@@ -44,9 +44,9 @@ extern "C" int emu_run(const help_b200_batch* b, float* monthly, float* yearly, 
   A.monthly = monthly; A.yearly = yearly; A.raw = raw; A.flags = flags; std::vector<int32_t> drow(n); for (int64_t c = 0; c < n; ++c) drow[c] = (int32_t)c;
   A.daily = g_daily; A.daily_row = g_daily ? drow.data() : nullptr; A.daily_days = g_daily_days;
 #ifdef HELP_DBG_CAPMEMO
-  for (int64_t c = 0; c < n; ++c) { blockIdx.x = (unsigned)c; memo2_newcell(); help_sim_kernel<67, 4>(A); }
+  for (int64_t c = 0; c < n; ++c) { blockIdx.x = (unsigned)c; memo2_newcell(); help_sim_kernel<67, 128, 128>(A); }
 #else
-  for (int64_t c = 0; c < n; ++c) { blockIdx.x = (unsigned)c; help_sim_kernel<67, 4>(A); }
+  for (int64_t c = 0; c < n; ++c) { blockIdx.x = (unsigned)c; help_sim_kernel<67, 128, 128>(A); }
 #endif
   return 0;
 }
