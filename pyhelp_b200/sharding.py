@@ -21,6 +21,45 @@ def shard_range(n_cells: int, world: int, rank: int) -> tuple[int, int]:
     return start, start + base + (1 if rank < rem else 0)
 
 
+def estimate_cost(batch: CellBatch) -> np.ndarray:
+    """Relative simulation cost of every cell, from its layer records alone (no GPU work):
+    ~ number of modelling segments (7 evaporative + 1..3 per layer by thickness, reference
+    ``HELP3O.FOR:1503-1616``) times 3 for a profile with a liner (barrier soil or geomembrane:
+    head, leakage and lateral-drainage iterations every sub-step; measured on B200: a
+    drain-over-barrier cell costs ~3x, a double-liner landfill cover ~5x a natural-soil cell)."""
+    from . import _native as N
+    nlay = batch.cell_i32[N.HB_NLAY].astype(np.int64)
+    L = batch.max_layers
+    lay = np.arange(L)[:, None] < nlay[None, :]
+    thick = batch.layer_f32[N.HL_THICK]                       # cm (IU10 = 2) or inches
+    si = batch.cell_i32[N.HB_IU10] == 2
+    inches = np.where(si[None, :], thick / 2.54, thick)
+    nseg = 7 + np.where(lay, np.clip(np.ceil(inches / 18.0), 1, 3), 0).sum(axis=0)
+    ltype = batch.layer_i32[N.HL_TYPE]
+    liner = (lay & (ltype >= 3)).any(axis=0)
+    return nseg * np.where(liner, 3.0, 1.0)
+
+
+def cost_balanced_ranges(cost, world: int) -> list[tuple[int, int]]:
+    """Contiguous [start, stop) per rank with (nearly) equal total cost: every rank finishes at
+    the same time even when cheap and expensive profiles are clustered in the caller's order.
+    Equal costs reproduce :func:`shard_range` up to one cell."""
+    c = np.asarray(cost, dtype=np.float64).reshape(-1)
+    n = c.size
+    if n == 0:
+        return [(0, 0)] * world
+    pre = np.concatenate([[0.0], np.cumsum(c)])
+    cuts = [0]
+    for r in range(1, world):
+        k = int(np.searchsorted(pre, pre[-1] * r / world, side="left"))
+        # the cut that leaves the prefix closest to its target
+        if k > 0 and abs(pre[k - 1] - pre[-1] * r / world) <= abs(pre[min(k, n)] - pre[-1] * r / world):
+            k -= 1
+        cuts.append(min(max(k, cuts[-1]), n))
+    cuts.append(n)
+    return [(cuts[r], cuts[r + 1]) for r in range(world)]
+
+
 def compact_nodes(batch: CellBatch) -> CellBatch:
     """Drop the weather nodes no cell of this (sub-)batch references and renumber the rest, so a
     rank uploads ~W/world nodes instead of all W."""
@@ -40,20 +79,23 @@ def compact_nodes(batch: CellBatch) -> CellBatch:
     return out
 
 
-def shard_batch(batch: CellBatch, world: int, rank: int) -> CellBatch:
-    a, b = shard_range(batch.n_cells, world, rank)
+def shard_batch(batch: CellBatch, world: int, rank: int, by_cost: bool = False) -> CellBatch:
+    """Rank's contiguous shard (equal cell counts, or equal estimated cost with ``by_cost``)
+    with only the weather nodes it references."""
+    a, b = cost_balanced_ranges(estimate_cost(batch), world)[rank] if by_cost else shard_range(batch.n_cells, world, rank)
     return compact_nodes(batch.take(np.arange(a, b)))
 
 
-def gather_yearly(yearly_local, n_cells_total: int, world: int, rank: int, dst: int = 0):
+def gather_yearly(yearly_local, n_cells_total: int, world: int, rank: int, dst: int = 0, ranges=None):
     """Gather per-rank ``[5][Ny][n_local]`` tensors to ``dst``; returns ``[5][Ny][n_total]`` there
-    (caller's cell order, because shards are contiguous) and None elsewhere.  Works on CUDA
+    (caller's cell order, because shards are contiguous; ``ranges`` = the per-rank [start, stop)
+    when they are not the equal-count ones) and None elsewhere.  Works on CUDA
     tensors with the nccl backend and on CPU tensors with gloo."""
     import torch
     import torch.distributed as dist
     if world == 1:
         return yearly_local
-    sizes = [shard_range(n_cells_total, world, r) for r in range(world)]
+    sizes = list(ranges) if ranges is not None else [shard_range(n_cells_total, world, r) for r in range(world)]
     nmax = max(b - a for a, b in sizes)
     rows, ny = yearly_local.shape[0], yearly_local.shape[1]
     pad = torch.zeros((rows, ny, nmax), dtype=yearly_local.dtype, device=yearly_local.device)

@@ -82,3 +82,32 @@ def test_gather_yearly_gloo_world2(n_total):
     want = (np.arange(n_total, dtype=np.float32)[None, None, :] + 1000.0 * np.arange(5)[:, None, None]
             + 10.0 * np.arange(3)[None, :, None])
     assert got.shape == (5, 3, n_total) and np.array_equal(got, want)
+
+
+def test_cost_balanced_ranges():
+    # equal costs: the equal-count split (up to one cell)
+    r = sharding.cost_balanced_ranges(np.ones(10), 3)
+    assert r[0][0] == 0 and r[-1][1] == 10 and all(a[1] == b[0] for a, b in zip(r, r[1:]))
+    assert sorted(b - a for a, b in r) in ([3, 3, 4], [3, 4, 3])
+    # expensive cells clustered at the end: the last rank gets fewer cells, every rank ~ the same cost
+    cost = np.concatenate([np.ones(900), 5 * np.ones(100)])
+    r = sharding.cost_balanced_ranges(cost, 4)
+    tot = [cost[a:b].sum() for a, b in r]
+    assert max(tot) - min(tot) <= 5.0 and (r[3][1] - r[3][0]) < (r[0][1] - r[0][0])
+    assert sharding.cost_balanced_ranges([], 2) == [(0, 0), (0, 0)]
+    assert sharding.cost_balanced_ranges([1.0], 3)[-1][1] == 1
+
+
+def test_estimated_cost_ranks_liner_profiles_above_natural_soil():
+    from pyhelp_b200 import grid as G, synth
+    n = 64
+    g, ex = synth.grid_landfill(n, seed=3)
+    wx = synth.synth_weather(2, 2001, 1, seed=1)
+    node = synth.assign_nodes(n, 2)
+    bl = G.batch_from_grid(g, wx["years_of_day"], wx["precip"], wx["airtemp"], wx["solrad"], node, node, node, extra_layers=ex)
+    bn = G.batch_from_grid(synth.grid_natural_3layer(n, seed=3), wx["years_of_day"], wx["precip"], wx["airtemp"], wx["solrad"],
+                           node, node, node)
+    cl, cn = sharding.estimate_cost(bl), sharding.estimate_cost(bn)
+    assert cl.shape == cn.shape == (n,) and cl.min() > cn.max() and (cn >= 8).all() and (cn <= 16).all()
+    sh = sharding.shard_batch(bn, 2, 1, by_cost=True)
+    assert abs(sh.n_cells - n // 2) <= 6
