@@ -205,6 +205,10 @@ __host__ __device__ __forceinline__ void r8_pow_sb(double x, double y0, double y
   const helpmath::Pair R = helpmath::det_pow_samebase(x, y0, y1);   // x**y0 and x**y1, same bits as two r8_pow calls
   r0 = R.a; r1 = R.b;
 }
+__host__ __device__ __forceinline__ void r8_log_pair(double x, double& hi, double& lo) { helpmath::det_log_pair(x, hi, lo); }
+__host__ __device__ __forceinline__ double r8_pow_logbase(double x, double hi, double lo, double y) {
+  return helpmath::det_pow_logbase(x, hi, lo, y);   // x**y, same bits as r8_pow, logarithm of x supplied
+}
 __host__ __device__ __forceinline__ double r8_log(double x) { return helpmath::det_log(x); }
 __host__ __device__ __forceinline__ double r8_atan(double x) { return helpmath::det_atan(x); }
 __host__ __device__ __forceinline__ double r8_sin(double x) { return helpmath::det_sin(x); }

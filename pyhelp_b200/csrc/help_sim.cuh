@@ -71,7 +71,21 @@ __device__ __forceinline__ float f73(float v, uint32_t& flag) {
 __constant__ int kICAL[13] = {0, 31, 59, 90, 120, 151, 181, 212, 243, 273, 304, 334, 365};
 
 // ---- geomembrane leakage (FML, F:4870-5304) ------------------------------------
-struct FmlC { int lcase, lpq, ltype; float thklin, phole, defec, trans; double rclin, rcs, dth; };
+struct FmlC {
+  int lcase, lpq, ltype; float thklin, phole, defec, trans; double rclin, rcs, dth;
+  double rcs_ek;   // RCS**ek of the Giroud formulas (F:5010-5160): a constant of the liner, evaluated once per cell
+};
+
+// contact-quality constants of the Giroud wetted-radius formulas; form 3 only
+__device__ __forceinline__ bool fml_giroud(int LC, int PQ, float& cp, float& cd, float& eh, float& ek) {
+  if (LC == 2 && PQ > 1 && PQ < 5) { cp = 0.00363f; cd = 0.0229f; eh = 0.38f; ek = -0.25f; return true; }
+  if (LC == 3 || LC == 4) {
+    if (PQ == 2) { cp = 0.052f; cd = 0.0663f; eh = 0.5f; ek = -0.06f; return true; }
+    if (PQ == 3) { cp = 0.0449f; cd = 0.0572f; eh = 0.45f; ek = -0.13f; return true; }
+    if (PQ == 4) { cp = 0.1053f; cd = 0.134f; eh = 0.45f; ek = -0.13f; return true; }
+  }
+  return false;
+}
 
 __device__ __noinline__ double fml_leakage(const FmlC& P, double TH) {
   double QVAPOR = 0.0, RPHOLE = 0.0, RDEFEC = 0.0, HPHOLE = 0.0, HDEFEC = 0.0;
@@ -111,13 +125,16 @@ __device__ __noinline__ double fml_leakage(const FmlC& P, double TH) {
       QPHOLE = (float)((double)(P.phole * 0.000671f) * head * RCS);
       QDEFEC = (float)((double)(P.defec * 0.00758f) * head * RCS);
     } else if (form == 3) {
+      // head**eh is shared by the two formulas, RCS**ek is a constant of the liner (same bits as
+      // evaluating each power where the reference writes it)
+      const double ph = r8_pow(head, (double)eh), pr = P.rcs_ek;
       if (P.phole > 0.0f) {
-        RPHOLE = (double)cp * r8_pow(head, (double)eh) * r8_pow(RCS, (double)ek);
+        RPHOLE = (double)cp * ph * pr;
         HPHOLE = 1.0 + (head / (2.0 * DTH * r8_log(RPHOLE / (double)0.0005f)));
         QPHOLE = (float)((double)(P.phole * 26.4f) * RCS * HPHOLE * (RPHOLE * RPHOLE));
       }
       if (P.defec > 0.0f) {
-        RDEFEC = (double)cd * r8_pow(head, (double)eh) * r8_pow(RCS, (double)ek);
+        RDEFEC = (double)cd * ph * pr;
         HDEFEC = 1.0 + (head / (2.0 * DTH * r8_log(RDEFEC / (double)0.00564f)));
         QDEFEC = (float)((double)(P.defec * 26.4f) * RCS * HDEFEC * (RDEFEC * RDEFEC));
       }
@@ -168,9 +185,26 @@ __device__ __noinline__ double fml_leakage(const FmlC& P, double TH) {
   return Q;
 }
 
+struct LatC { double dslope, dxleng, alpha, sa, ca, A, B, C, D, lbh, lbl; };   // constants of LATFLO (F:4686-4712) for one drain layer
+// LATFLO's slope/length terms (F:4686-4712): they depend on the drain layer only
+__device__ __forceinline__ LatC lateral_consts(float slope_pct, float xleng_ft) {
+  LatC L;
+  const double PI = 3.141592654;
+  L.dslope = (double)slope_pct / 100.0;
+  L.dxleng = (double)xleng_ft * 12.0;
+  if (L.dxleng == 0.0) L.dxleng = 1.0;
+  L.alpha = r8_atan(L.dslope);
+  L.sa = r8_sin(L.alpha); L.ca = r8_cos(L.alpha);
+  L.A = PI / 4.0 / L.ca;
+  L.B = 2.0 * r8_sqrt(0.4) / PI;
+  L.C = 0.4 * (L.sa * L.sa);
+  L.D = 0.5 / r8_log(L.B);
+  r8_log_pair(L.B, L.lbh, L.lbl);            // B is the base of a power in every LATFLO iteration
+  return L;
+}
+
 // ---- lateral drainage rate for a head TH (LATKS + LATFLO, F:4626-4734) --------------
-__device__ __noinline__ double lateral_rate(const Image& img, int64_t s, int NSEGB, int NSEGL, double TH,
-                                            float slope_pct, float xleng_ft) {
+__device__ __noinline__ double lateral_rate(const Image& img, int64_t s, int NSEGB, int NSEGL, double TH, const LatC& L) {
   double ELKS = 0.0;
   {
     double H = TH;
@@ -183,23 +217,14 @@ __device__ __noinline__ double lateral_rate(const Image& img, int64_t s, int NSE
     }
   }
   const double EPS = 0.030, PI = 3.141592654;
-  const double DSLOPE = (double)slope_pct / 100.0;
-  double DXLENG = (double)xleng_ft * 12.0;
-  if (DXLENG == 0.0) DXLENG = 1.0;
-  const double ALPHA = r8_atan(DSLOPE);
-  const double YSTAR = TH / DXLENG;
-  double QSTAR = 2.0 * YSTAR * r8_sin(ALPHA) * r8_cos(ALPHA);
-  if (ALPHA <= 0.0) { const double t = (4.0 / PI) * YSTAR; return (t * t) * ELKS; }
-  const double A = PI / 4.0 / r8_cos(ALPHA);
-  const double B = 2.0 * r8_sqrt(0.4) / PI;
-  const double sa = r8_sin(ALPHA);
-  const double C = 0.4 * (sa * sa);
-  const double D = 0.5 / r8_log(B);
-  if (YSTAR < ((double)0.2f * DSLOPE)) return QSTAR * ELKS;
+  const double YSTAR = TH / L.dxleng;
+  double QSTAR = 2.0 * YSTAR * L.sa * L.ca;
+  if (L.alpha <= 0.0) { const double t = (4.0 / PI) * YSTAR; return (t * t) * ELKS; }
+  if (YSTAR < ((double)0.2f * L.dslope)) return QSTAR * ELKS;
   float QSTARN;
   int ITER = 1;
   for (;;) {
-    const double Fq = A * r8_pow(B, r8_pow(QSTAR / C, D));
+    const double Fq = L.A * r8_pow_logbase(L.B, L.lbh, L.lbl, r8_pow(QSTAR / L.C, L.D));
     QSTARN = (float)((YSTAR * YSTAR) / (Fq * Fq));
     const double TOLER = 2.0 * fabs((double)QSTARN - QSTAR) / ((double)QSTARN + QSTAR);
     if (EPS < TOLER && ITER < 10) { ITER = ITER + 1; QSTAR = (QSTAR + (double)QSTARN) / 2.0; continue; }
@@ -217,7 +242,9 @@ struct ProfC {
   int n, NSEGB, NSEGE, NSEG, nstep, ibar, lat, subin;
   float drculs, dthics, slope, xleng, sublin;
   FmlC fml;
+  LatC latc;
 };
+
 
 // Per-cell segment state, one object so that the routing function addresses all of it from one
 // pointer: SB[j] = {SW, BAL} of segment j (always read and written together: one 16-byte
@@ -281,7 +308,7 @@ __device__ __noinline__ RouteOut route_subprofile(const Image& img, int64_t s, c
         // (IBAR 4/5 = bottom liner with subsurface inflow: the Fortran computes no leakage, F:4241-4242)
         if (IBAR == 1) QPERCY = (double)P.drculs * (THY + (double)P.dthics) / (double)P.dthics;
         if (IBAR == 2) QPERCY = fml_leakage(P.fml, THY);
-        if (LAT == 1) QLATY = lateral_rate(img, s, NSEGB, NSEGL, THY, P.slope, P.xleng);
+        if (LAT == 1) QLATY = lateral_rate(img, s, NSEGB, NSEGL, THY, P.latc);
       }
     }
     // ---- AVROUT (F:4287-4527): top -> bottom ---------------------------------------------------
@@ -616,6 +643,11 @@ __global__ void __launch_bounds__(THREADS) __maxnreg__(REGS) help_sim_kernel(Sim
       p.fml.thklin = img.PF(P_THKLIN, N, s); p.fml.phole = img.PF(P_PHOLE, N, s);
       p.fml.defec = img.PF(P_DEFEC, N, s); p.fml.trans = img.PF(P_TRANS, N, s);
       p.fml.rclin = img.PD(D_RCLIN, N, s); p.fml.rcs = img.PD(D_RCS, N, s); p.fml.dth = (double)p.dthics;
+      {
+        float cp, cd, eh, ek = 0.f;
+        p.fml.rcs_ek = ((p.ibar == 2 || p.ibar == 5) && fml_giroud(p.fml.lcase, p.fml.lpq, cp, cd, eh, ek)) ? r8_pow(p.fml.rcs, (double)ek) : 0.0;
+        if (p.lat == 1) p.latc = lateral_consts(p.slope, p.xleng);
+      }
       RECIR[N] = img.PF(P_RECIR, N, s);
       LDn[N] = (N <= 5 && ns > 0) ? img.PI(Q_LD, N, s) : 0;
       e += ns;

@@ -51,6 +51,8 @@ static inline double r8_pow(double x, double y) { return pow(x, y); }
 static inline void r8_pow2(double x0, double y0, double x1, double y1, double& r0, double& r1) { r0 = pow(x0, y0); r1 = pow(x1, y1); }
 static inline void r8_pow_sb(double x, double y0, double y1, double& r0, double& r1) { r0 = pow(x, y0); r1 = pow(x, y1); }
 static inline double r8_log(double x) { return log(x); }
+static inline void r8_log_pair(double, double& hi, double& lo) { hi = lo = 0; }
+static inline double r8_pow_logbase(double x, double, double, double y) { return pow(x, y); }
 static inline double r8_atan(double x) { return atan(x); }
 static inline double r8_sin(double x) { return sin(x); }
 static inline double r8_cos(double x) { return cos(x); }
@@ -67,6 +69,8 @@ using helpmath::r4_exp; using helpmath::r4_log; using helpmath::r4_log10; using 
 using helpmath::r4_cos; using helpmath::r4_tan; using helpmath::r4_acos; using helpmath::r4_pow;
 using helpmath::r4_sqrt; using helpmath::r4_pow8; using helpmath::r4_pow7; using helpmath::r4_pow4;
 static inline double r8_log(double x) { return helpmath::det_log(x); }
+static inline void r8_log_pair(double x, double& hi, double& lo) { helpmath::det_log_pair(x, hi, lo); }
+static inline double r8_pow_logbase(double x, double hi, double lo, double y) { return helpmath::det_pow_logbase(x, hi, lo, y); }
 static inline double r8_atan(double x) { return helpmath::det_atan(x); }
 static inline double r8_sin(double x) { return helpmath::det_sin(x); }
 static inline double r8_cos(double x) { return helpmath::det_cos(x); }
