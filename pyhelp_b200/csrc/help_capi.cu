@@ -248,18 +248,18 @@ extern "C" int help_b200_engine_create(const help_b200_batch* b, int want_monthl
 }
 
 // Launch shapes of help_sim_kernel<16, ..> (help_sim.cuh): threads per SM they keep resident.
-static const int kShapeCap[3] = {512, 640, 768};
+static const int kShapeCap[4] = {512, 640, 768, 1024};
 // The shape for a batch of n cells: the fewest waves the largest shape allows, filled evenly,
 // with the most registers that still fit.  HELP_B200_SHAPE overrides (developer A/B runs).
 static int pick_shape(int64_t n, int device) {
-  if (const char* f = getenv("HELP_B200_SHAPE")) { const int v = atoi(f); if (v >= 0 && v <= 2) return v; }
+  if (const char* f = getenv("HELP_B200_SHAPE")) { const int v = atoi(f); if (v >= 0 && v <= 3) return v; }
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
   const int64_t need = (n + sms - 1) / sms;                     // threads per SM
-  const int64_t waves = (need + kShapeCap[2] - 1) / kShapeCap[2];
+  const int64_t waves = (need + kShapeCap[3] - 1) / kShapeCap[3];
   const int64_t per = (need + waves - 1) / (waves > 0 ? waves : 1);
-  for (int k = 0; k < 3; ++k) if (per <= kShapeCap[k]) return k;
-  return 2;
+  for (int k = 0; k < 4; ++k) if (per <= kShapeCap[k]) return k;
+  return 3;
 }
 
 template <int MAXSEG, int THREADS, int REGS>
@@ -297,7 +297,8 @@ extern "C" int help_b200_engine_simulate(help_b200_engine* e, void* stream) {
         switch (pick_shape(n, e->device)) {
           case 0: launch_sim<16, 128, 128>(A, n, st); break;
           case 1: launch_sim<16, 128, 96>(A, n, st); break;
-          default: launch_sim<16, 128, 80>(A, n, st); break;
+          case 2: launch_sim<16, 128, 80>(A, n, st); break;
+          default: launch_sim<16, 128, 64>(A, n, st); break;
         }
         break;
 #ifndef HELP_DEV_FAST_BUILD

@@ -574,7 +574,8 @@ struct Surf {      // REAL*4 surface-process state of one cell
 // instruction cache, and warps that run the same region together share its fetches
 // (measured on B200: +12 % throughput, profiles/r1_notes.md).
 // The kernel is compiled for several launch shapes (THREADS per block, REGS per thread ->
-// resident threads per SM: 128-thread blocks at 128 registers = 512, at 96 = 640, at 80 = 768): all cells of a launch take the same time, so the launcher (help_capi.cu pick_shape)
+// resident threads per SM: 128-thread blocks at 128 registers = 512, at 96 = 640, at 80 = 768, at
+// 64 = 1024; the per-cell cost is flat from 640 threads up, so what matters is one full wave): all cells of a launch take the same time, so the launcher (help_capi.cu pick_shape)
 // chooses the shape with the most registers that still fits the batch into the fewest,
 // evenly filled waves.
 #ifndef HELP_SIM_NO_DAYSYNC
