@@ -178,7 +178,7 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     g, wx, node = make_workload(0)
     wd = tempfile.mkdtemp(prefix="help_ref_")
-    per_core = 24
+    per_core = 64
     rates, times = [], []
     for it in range(args.warmup + args.steps):
         r, dt, ns = cpu_oracle_rate(g, wx, node, cores, per_core, "glibc", wd)
@@ -327,7 +327,7 @@ def run_ours(args):
         if world == 1:
             cores = os.cpu_count() or 1
             wd = tempfile.mkdtemp(prefix="help_cpu_")
-            rate, cdt, ns = cpu_oracle_rate(g, wx, node, cores, 16, "det", wd)
+            rate, cdt, ns = cpu_oracle_rate(g, wx, node, cores, 96, "det", wd)
             line["cpu_baseline"] = {"value": rate, "unit": "cell-years/s", "cores": cores, "kind": "port",
                                     "sample": f"first {ns} cells x {N_YEARS} yr of the same workload, Pool({cores}), {cdt:.1f} s"}
         print(json.dumps(line), flush=True)
