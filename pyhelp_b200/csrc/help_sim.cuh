@@ -321,14 +321,13 @@ __device__ __noinline__ RouteOut route_subprofile(const Image& img, int64_t s, c
     { const double2 sb = SS.SB[NSEGB]; swj = sb.x; balj = sb.y; }
     double drin = DRINa(NSEGB);
     for (int J = NSEGB; J <= NSEGL; ++J, p += kRecBytes) {
-      float4 A1 = A, B1 = B;
-      double2 C1 = Cv, D1 = Dv;
-      double sw1 = 0.0, bal1 = 0.0;
-      if (J < NSEGL) {
-        const char* p1 = p + kRecBytes;
-        A1 = rec_f4<RV_A>(p1); B1 = rec_f4<RV_B>(p1); C1 = rec_d2<RV_C>(p1); D1 = rec_d2<RV_D>(p1);
-        { const double2 sb = SS.SB[J + 1]; sw1 = sb.x; bal1 = sb.y; }
-      }
+      // Unconditional loads from an always-valid address (the last segment reloads itself): a
+      // conditional load needs a select on its result, which waits for the data at once.
+      const char* p1 = (J < NSEGL) ? p + kRecBytes : p;
+      const float4 A1 = rec_f4<RV_A>(p1), B1 = rec_f4<RV_B>(p1);
+      const double2 C1 = rec_d2<RV_C>(p1), D1 = rec_d2<RV_D>(p1);
+      const double2 sb1 = SS.SB[J + 1];              // (SB has MAXSEG + 2 entries)
+      const double sw1 = sb1.x, bal1 = sb1.y;
 #ifndef HELP_LAZY_E
       const double2 Ev = rec_d2<RV_E>(p);                 // {B of the Newton solve, LOW at WP}
 #endif
@@ -508,13 +507,13 @@ __device__ __noinline__ RouteOut route_subprofile(const Image& img, int64_t s, c
       float ulf = rec_f4<RV_A>(pk).x;
       for (int Kk = NSEGL; Kk >= NSEGB; --Kk) {
         const double sub = has_sub ? (double)rec_tail(pk).subin * DT : 0.0;
-        double din_n = 0.0, swk_n = 0.0, balk_n = 0.0;
-        float ulf_n = 0.0f;
-        if (Kk > NSEGB) {                        // the loads of the next segment up, ahead of their use
-          pk -= kRecBytes;
-          din_n = DRINa(Kk - 1); ulf_n = rec_f4<RV_A>(pk).x;
-          { const double2 sb = SS.SB[Kk - 1]; swk_n = sb.x; balk_n = sb.y; }
-        }
+        // the loads of the next segment up, ahead of their use; unconditional (Kk-1 >= 0 is a
+        // valid index of SB and DRIN, the record pointer stays on the top segment)
+        if (Kk > NSEGB) pk -= kRecBytes;
+        const double din_n = DRINa(Kk - 1);
+        const float ulf_n = rec_f4<RV_A>(pk).x;
+        const double2 sbn = SS.SB[Kk - 1];
+        const double swk_n = sbn.x, balk_n = sbn.y;
         const double ul = (double)ulf;
         const double Ek = (Kk <= 7) ? Ed[Kk] : 0.0;
         double BALT = PLAIN ? (din - dnext - Ek) : (din + sub - dnext - Ek);
