@@ -175,8 +175,14 @@ struct Image {
 #if defined(__CUDA_ARCH__)
 template <int V> __device__ __forceinline__ float4 rec_f4(const char* p) { return __ldg((const float4*)(p + V * 512)); }
 template <int V> __device__ __forceinline__ double2 rec_d2(const char* p) { return __ldg((const double2*)(p + V * 512)); }
+// bring the vectors of a segment into L1 without tying up registers
+__device__ __forceinline__ void rec_prefetch(const char* p) {
+#pragma unroll
+  for (int v = 0; v <= RV_E; ++v) asm volatile("prefetch.global.L1 [%0];" ::"l"(p + v * 512));
+}
 #else
 template <int V> inline float4 rec_f4(const char* p) { return *(const float4*)(p + V * 512); }
+inline void rec_prefetch(const char*) {}
 template <int V> inline double2 rec_d2(const char* p) { return *(const double2*)(p + V * 512); }
 #endif
 __host__ __device__ __forceinline__ RecTail rec_tail(const char* p) { return *(const RecTail*)(p + RV_F * 512); }

@@ -312,25 +312,21 @@ __device__ __noinline__ RouteOut route_subprofile(const Image& img, int64_t s, c
       }
     }
     // ---- AVROUT (F:4287-4527): top -> bottom ---------------------------------------------------
-    // The record vectors and the state of segment J+1 are loaded at the top of iteration J:
-    // the capillary limit of J needs them, and they are segment J's own in the next iteration.
+    // Nothing is carried from one segment to the next across the powers (register pressure):
+    // segment J's own vectors are loaded at the top of its iteration -- L1 hits, they were
+    // prefetched one iteration earlier -- segment J+1's are prefetched now and loaded where the
+    // capillary limit of J needs them.  (Carrying J+1's vectors in registers into the next
+    // iteration measured 0..5 % slower at every register budget.)
     const char* p = p0;
-    float4 A = rec_f4<RV_A>(p), B = rec_f4<RV_B>(p);
-    double2 Cv = rec_d2<RV_C>(p), Dv = rec_d2<RV_D>(p);
-    double swj, balj;
-    { const double2 sb = SS.SB[NSEGB]; swj = sb.x; balj = sb.y; }
     double drin = DRINa(NSEGB);
     for (int J = NSEGB; J <= NSEGL; ++J, p += kRecBytes) {
-      // Unconditional loads from an always-valid address (the last segment reloads itself): a
-      // conditional load needs a select on its result, which waits for the data at once.
-      const char* p1 = (J < NSEGL) ? p + kRecBytes : p;
-      const float4 A1 = rec_f4<RV_A>(p1), B1 = rec_f4<RV_B>(p1);
-      const double2 C1 = rec_d2<RV_C>(p1), D1 = rec_d2<RV_D>(p1);
-      const double2 sb1 = SS.SB[J + 1];              // (SB has MAXSEG + 2 entries)
-      const double sw1 = sb1.x, bal1 = sb1.y;
-#ifndef HELP_LAZY_E
+      const char* p1 = (J < NSEGL) ? p + kRecBytes : p;        // always a valid record
+      const float4 A = rec_f4<RV_A>(p), B = rec_f4<RV_B>(p);
+      const double2 Cv = rec_d2<RV_C>(p), Dv = rec_d2<RV_D>(p);
+      const double2 sbj = SS.SB[J];
+      const double swj = sbj.x, balj = sbj.y;
+      rec_prefetch(p1);
       const double2 Ev = rec_d2<RV_E>(p);                 // {B of the Newton solve, LOW at WP}
-#endif
       const double ul = (double)A.x, rs = (double)A.y, wp = (double)A.z, fc = (double)A.w;
       const double rspan = Cv.x, kdt = Cv.y;
       const double span = ul - rs;
@@ -354,6 +350,10 @@ __device__ __noinline__ RouteOut route_subprofile(const Image& img, int64_t s, c
       if (kind == 0) {
         // F:4330-4340 == F:4356-4366: matric potential of J+1 (Brooks-Corey) carried to J,
         // clipped to [WP, FC]; then LOW = K dt Theta(SWLIM)^C (F:4420-4421)
+        const float4 A1 = rec_f4<RV_A>(p1), B1 = rec_f4<RV_B>(p1);
+        const double2 C1 = rec_d2<RV_C>(p1), D1 = rec_d2<RV_D>(p1);
+        const double2 sb1 = SS.SB[J + 1];              // (SB has MAXSEG + 2 entries)
+        const double sw1 = sb1.x, bal1 = sb1.y;
         const double ul1 = (double)A1.x, rs1 = (double)A1.y, bub1 = (double)B1.y;
         const double bub = (double)B.y, lam = (double)B.x;
         const double base1 = sw1 + (bal1 / 2.0);
@@ -371,11 +371,7 @@ __device__ __noinline__ RouteOut route_subprofile(const Image& img, int64_t s, c
         swl = (double)SWLIM;
         LOW = kdt * r8_pow(fdiv_by(swl - rs, span, rspan), Dv.x);
       }
-#ifndef HELP_LAZY_E
       else if (kind == 1) { swl = wp; LOW = Ev.y; }
-#else
-      else if (kind == 1) { swl = wp; LOW = rec_d2<RV_E>(p).y; }
-#endif
       else if (kind == 2) { swl = fc; LOW = LOWFC_L; }
       else { swl = ul; LOW = kdt; }            // ((ul - rs)/(ul - rs))**C == 1
       const double base = swj + (balj / 2.0);                     // storage at the start of the step
@@ -439,11 +435,7 @@ __device__ __noinline__ RouteOut route_subprofile(const Image& img, int64_t s, c
             // constant of the segment (set-up kernel).  x^C and x^(C-1) share one logarithm.
             double An = PLAIN ? (2.0 * (swj - rs) + balj + drin - Ej) : (2.0 * (swj - rs) + balj + drin + DSUBj - Ej);
             if (add_sub) An = An + (2.0 * DSUBE);
-#ifndef HELP_LAZY_E
             const double Bc = Ev.x;
-#else
-            const double Bc = rec_d2<RV_E>(p).x;
-#endif
             const double TOLER = 0.003 * span;
             const double ftol = (double)0.3f * TOLER;
             const double Cm1 = C - 1.0;
@@ -474,6 +466,9 @@ __device__ __noinline__ RouteOut route_subprofile(const Image& img, int64_t s, c
       if (out > DRNMAX) out = DRNMAX;
       if (out < 0.0) out = 0.0;
       if (J < NSEGL && (above & 2)) {
+        const float4 A1 = rec_f4<RV_A>(p1);
+        const double2 C1 = rec_d2<RV_C>(p1), sb1 = SS.SB[J + 1];
+        const double sw1 = sb1.x, bal1 = sb1.y;
         const double kdt1 = C1.y;
         if (out > kdt1) {
           const RecTail t0 = rec_tail(p), t1 = rec_tail(p + kRecBytes);
@@ -492,7 +487,7 @@ __device__ __noinline__ RouteOut route_subprofile(const Image& img, int64_t s, c
         }
       }
       DRINa(J + 1) = out;
-      A = A1; B = B1; Cv = C1; Dv = D1; swj = sw1; balj = bal1; drin = out;
+      drin = out;
     }
     // F:4518-4525 and PROFIL (F:4535-4574) fused: new balance bottom -> top, pushing
     // water above saturation into the segment above

@@ -4,7 +4,7 @@ import os, sys, subprocess
 import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__)); ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT); sys.path.insert(0, HERE)
-subprocess.check_call("g++ -O2 -mfma -ffp-contract=off -std=c++17 -shared -fPIC emu.cpp -o libemu.so", shell=True, cwd=HERE)
+subprocess.check_call("g++ -O2 -mfma -ffp-contract=off -std=c++17 -shared -fPIC %s emu.cpp -o libemu.so" % os.environ.get("EMU_FLAGS", ""), shell=True, cwd=HERE)
 from pyhelp_b200 import synth, inputs
 from oracle import oracle
 import run_emu
