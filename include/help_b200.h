@@ -164,6 +164,10 @@ int help_b200_device_count(void);
  * multiprocessing.Pool(ncore) (pyhelp/processing.py:43-47).                    */
 int help_b200_set_device(int device);
 const char* help_b200_last_error(void);
+/* The library keeps freed device memory in the device's stream-ordered pool so that the next
+ * batch re-uses it (the reference's workers likewise stay alive between cells,
+ * pyhelp/processing.py:43-47); this hands it back to the driver.                            */
+int help_b200_release_memory(void);
 /* algorithmic bytes one simulate() moves:
  * 12*W*D + (56+36*L)*N + 336*N*Y, W = distinct nodes referenced, D = days     */
 double help_b200_algorithmic_bytes(const help_b200_batch* batch);

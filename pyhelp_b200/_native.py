@@ -92,6 +92,7 @@ def lib():
                                            C.POINTER(C.c_int32)]
     L.help_b200_engine_destroy.restype = None
     L.help_b200_engine_destroy.argtypes = [C.c_void_p]
+    L.help_b200_release_memory.restype = C.c_int
     L.help_b200_set_device.restype = C.c_int
     L.help_b200_set_device.argtypes = [C.c_int]
     L.help_b200_math_eval.restype = C.c_int

@@ -45,13 +45,33 @@ int fail(int code, const char* what, cudaError_t ce = cudaSuccess) {
     if (_e != cudaSuccess) return fail(_e == cudaErrorMemoryAllocation ? HELP_B200_ENOMEM : HELP_B200_ECUDA, #call, _e); \
   } while (0)
 
+// Device memory comes from the device's default stream-ordered pool, which is told to keep what
+// is freed (release threshold = max): a caller that runs batch after batch through
+// help_b200_run() -- create, simulate, fetch, destroy -- re-uses the same ~1.5 GB instead of
+// paying cudaMalloc/cudaFree (tens of ms, sporadically most of a second) every call.
+// help_b200_release_memory() hands the cached memory back to the driver.
+static void pool_setup() {
+  static int done_for = -1;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev == done_for) return;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    uint64_t keep = UINT64_MAX;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  }
+  done_for = dev;
+}
+
 template <typename T>
 int dev_alloc(T** p, size_t count) {
   *p = nullptr;
   if (count == 0) count = 1;
-  CU(cudaMalloc((void**)p, count * sizeof(T)));
+  pool_setup();
+  CU(cudaMallocAsync((void**)p, count * sizeof(T), (cudaStream_t)0));
+  CU(cudaStreamSynchronize((cudaStream_t)0));        // usable from any stream from here on
   return 0;
 }
+static void dev_free(void* p) { if (p) cudaFreeAsync(p, (cudaStream_t)0); }
 
 __global__ void iota_kernel(int32_t* p, int64_t n) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -94,7 +114,8 @@ static void engine_free(help_b200_engine* e) {
                   e->d_cell_f32, e->d_layer_f32, e->d_cell_i32, e->d_layer_i32, e->d_layer_rc, e->d_img_f32,
                   e->d_img_i32, e->d_img_f64, e->d_img_rec, e->d_monthly, e->d_yearly, e->d_raw, e->d_flags, e->d_topo,
                   e->d_key, e->d_key2, e->d_perm, e->d_iota, e->d_cub, e->d_daily, e->d_daily_row};
-  for (void* p : ptrs) if (p) cudaFree(p);
+  cudaDeviceSynchronize();                    // nothing of this engine is in flight when its memory returns to the pool
+  for (void* p : ptrs) dev_free(p);
   for (auto& ev : e->ev) if (ev) cudaEventDestroy(ev);
   if (e->stream) cudaStreamDestroy(e->stream);
   delete e;
@@ -143,6 +164,16 @@ extern "C" int help_b200_device_count(void) {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
   return n;
+}
+
+extern "C" int help_b200_release_memory(void) {
+  if (help_b200_device_count() < 1) return fail(HELP_B200_ENODEV, "no CUDA device");
+  int dev = 0; cudaMemPool_t pool;
+  CU(cudaGetDevice(&dev));
+  CU(cudaDeviceSynchronize());
+  CU(cudaDeviceGetDefaultMemPool(&pool, dev));
+  CU(cudaMemPoolTrimTo(pool, 0));
+  return 0;
 }
 
 extern "C" int help_b200_set_device(int device) {
@@ -201,7 +232,7 @@ extern "C" int help_b200_engine_create(const help_b200_batch* b, int want_monthl
   TRY(dev_alloc(&e->d_key, n)); TRY(dev_alloc(&e->d_key2, n)); TRY(dev_alloc(&e->d_perm, n)); TRY(dev_alloc(&e->d_iota, n));
   CUB_(cub::DeviceRadixSort::SortPairs(nullptr, e->cub_bytes, e->d_key, e->d_key2, e->d_iota, e->d_perm, (int)n, 0, 64,
                                        e->stream));
-  CUB_(cudaMalloc(&e->d_cub, e->cub_bytes ? e->cub_bytes : 1));
+  { uint8_t* q = nullptr; TRY(dev_alloc(&q, e->cub_bytes ? e->cub_bytes : 1)); e->d_cub = q; }
   // ---- upload (timed) -----------------------------------------------------------------
   cudaStream_t st = e->stream;
   CUB_(cudaEventRecord(e->ev[0], st));
@@ -366,8 +397,9 @@ extern "C" int help_b200_engine_select_daily(help_b200_engine* e, const int32_t*
   if (!e) return fail(HELP_B200_EINVAL, "engine is NULL");
   if (n_selected < 0 || (n_selected > 0 && !cells)) return fail(HELP_B200_EINVAL, "select_daily: bad argument");
   CU(cudaSetDevice(e->device));
-  if (e->d_daily) { cudaFree(e->d_daily); e->d_daily = nullptr; }
-  if (e->d_daily_row) { cudaFree(e->d_daily_row); e->d_daily_row = nullptr; }
+  cudaDeviceSynchronize();
+  if (e->d_daily) { dev_free(e->d_daily); e->d_daily = nullptr; }
+  if (e->d_daily_row) { dev_free(e->d_daily_row); e->d_daily_row = nullptr; }
   e->n_daily = 0;
   if (n_selected == 0) return 0;
   std::vector<int32_t> row((size_t)e->n, -1);
@@ -412,7 +444,8 @@ extern "C" int help_b200_engine_post_process(help_b200_engine* e, const int32_t*
   int32_t* d_ctx = nullptr; int8_t* d_mode = nullptr; double *d_cy = nullptr, *d_area = nullptr; int32_t* d_nnan = nullptr;
   int rc = 0;
   auto done = [&](int code) {
-    for (void* p : {(void*)d_ctx, (void*)d_mode, (void*)d_cy, (void*)d_area, (void*)d_nnan}) if (p) cudaFree(p);
+    cudaDeviceSynchronize();
+    for (void* p : {(void*)d_ctx, (void*)d_mode, (void*)d_cy, (void*)d_area, (void*)d_nnan}) dev_free(p);
     return code;
   };
   if ((rc = dev_alloc(&d_mode, (size_t)n)) || (rc = dev_alloc(&d_area, (size_t)7 * ny * 12)) || (rc = dev_alloc(&d_nnan, 1)) ||
@@ -485,7 +518,7 @@ extern "C" int help_b200_math_eval(int fn, const double* x, const double* y, dou
   if (n == 0) return 0;
   double *dx = nullptr, *dy = nullptr, *d_out = nullptr;
   int rc = 0;
-  auto done = [&](int code) { if (dx) cudaFree(dx); if (dy) cudaFree(dy); if (d_out) cudaFree(d_out); return code; };
+  auto done = [&](int code) { cudaDeviceSynchronize(); dev_free(dx); dev_free(dy); dev_free(d_out); return code; };
   if ((rc = dev_alloc(&dx, (size_t)n)) || (rc = dev_alloc(&d_out, (size_t)n)) || (y && (rc = dev_alloc(&dy, (size_t)n)))) return done(rc);
   cudaError_t ce = cudaMemcpy(dx, x, sizeof(double) * n, cudaMemcpyHostToDevice);
   if (ce == cudaSuccess && y) ce = cudaMemcpy(dy, y, sizeof(double) * n, cudaMemcpyHostToDevice);
@@ -508,7 +541,8 @@ extern "C" int help_b200_nearest_nodes(int64_t n_cells, const double* cell_lat, 
   NodeVec* d_vec = nullptr; int32_t* d_out = nullptr;
   int rc = 0;
   auto done = [&](int code) {
-    for (void* p : {(void*)d_clat, (void*)d_clon, (void*)d_nlat, (void*)d_nlon, (void*)d_vec, (void*)d_out}) if (p) cudaFree(p);
+    cudaDeviceSynchronize();
+    for (void* p : {(void*)d_clat, (void*)d_clon, (void*)d_nlat, (void*)d_nlon, (void*)d_vec, (void*)d_out}) dev_free(p);
     return code;
   };
   if ((rc = dev_alloc(&d_clat, (size_t)n_cells)) || (rc = dev_alloc(&d_clon, (size_t)n_cells)) || (rc = dev_alloc(&d_nlat, (size_t)n_nodes)) ||
