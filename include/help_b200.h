@@ -119,7 +119,7 @@ enum { HY_PRECIP = 0, HY_RUNOFF, HY_EVAPO, HY_LATDRAIN, HY_RECHG, HY_NROWS };
 #define HELP_B200_FLAG_NONCONV   0x1u  /* Newton solve hit 100 iterations (F:4481)     */
 #define HELP_B200_FLAG_NAN       0x2u  /* a NaN reached the monthly output             */
 #define HELP_B200_FLAG_OVERFLOW  0x4u  /* a value does not fit F7.3 (reference prints *******) */
-#define HELP_B200_FLAG_RECIRC    0x8u  /* design recirculates drainage into a layer: not simulated */
+#define HELP_B200_FLAG_RECIRC    0x8u  /* informational: the design recirculates drainage into a layer (RECIRC, HELP3O.FOR:5311-5440) */
 #define HELP_B200_FLAG_BADCELL   0x10u /* malformed design (no layers, NSEG > capacity ...) */
 
 typedef struct help_b200_result {

@@ -69,6 +69,7 @@ enum ImgSF : int {
   S_SUBIN,       // SUBINS   subsurface inflow, in/day
   S_SW0,         // SWUL     initial storage
   S_RELMIN,      // REAL*4 (WPUL - RSUL)/(UL - RSUL): RELMIN of F:4329, a constant of the segment
+  S_RCW,         // recirculation: THICK(K) of the receiving layer (mode 1) or the REAL*4 share (mode 2), see SI2
   S_NF
 };
 // ---- f64 per segment: constants of the routing loop that cost a division or a pow ---------------
@@ -103,6 +104,7 @@ enum ImgPI : int {
   Q_LPQ,         // LPQ(n)
   Q_LTYPE,       // LAYER(LP(n)) (F:5292)
   Q_LD,          // LD(n)
+  Q_RCRT,        // LAYR(LD(n)): layer the recirculated drainage of subprofile n returns to, 0 = none (F:5325-5340)
   Q_SUBIN,       // bit0: a segment of the subprofile has subsurface inflow (SUBINS > 0);
                  // bit1: "plain" subprofile: IBAR = 0, no inflow, not above a drain layer
   Q_NF
@@ -146,7 +148,7 @@ struct Image {
   __host__ __device__ static int64_t rec_bytes(int64_t stride, int segcap) { return (stride / 32) * (int64_t)segcap * kRecBytes; }
 
   __host__ __device__ static int64_t n_f32(int segcap) { return F_NSCALAR + P_NF * kNProf + (int64_t)S_NF * segcap; }
-  __host__ __device__ static int64_t n_i32(int segcap) { return I_NSCALAR + Q_NF * kNProf + segcap; }
+  __host__ __device__ static int64_t n_i32(int segcap) { return I_NSCALAR + Q_NF * kNProf + 2 * (int64_t)segcap; }
   __host__ __device__ static int64_t n_f64(int segcap) { return D_NF * kNProf + (int64_t)SD_NF * segcap; }
 
   __device__ __forceinline__ float& F(int f, int64_t c) const { return f32[(int64_t)f * stride + c]; }
@@ -159,6 +161,11 @@ struct Image {
   __device__ __forceinline__ int32_t& I(int f, int64_t c) const { return i32[(int64_t)f * stride + c]; }
   __device__ __forceinline__ int32_t& PI(int f, int n, int64_t c) const {
     return i32[(int64_t)(I_NSCALAR + f * kNProf + (n - 1)) * stride + c];
+  }
+  // recirculation plan of segment j (RECIRC, F:5392-5436): low byte = mode (0 none, 1 RCRI*DTHICK(j)/THICK(K),
+  // 2 RCRI*share, 3 RCRI), next byte = receiving layer K
+  __device__ __forceinline__ int32_t& SI2(int j, int64_t c) const {
+    return i32[(int64_t)(I_NSCALAR + Q_NF * kNProf + segcap + (j - 1)) * stride + c];
   }
   __device__ __forceinline__ int32_t& SI(int j, int64_t c) const {
     return i32[(int64_t)(I_NSCALAR + Q_NF * kNProf + (j - 1)) * stride + c];

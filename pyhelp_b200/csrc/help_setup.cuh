@@ -65,6 +65,7 @@ struct Segs {
       BUBUL[70], SUBINS[70], RCULS[70];
   int LAYSEG1[70], LAYSEG2[70], LSEG[70];
   int NSEGn[7], NSEG;
+  int LS1[23], LS2[23];     // LSEGS(K,1..2): first and last segment of layer K (F:1938-2022)
 };
 struct Topo {
   int LP[8], LD[8], LPQ[8], LCASE[8], NSTEP[8];
@@ -278,17 +279,20 @@ __device__ inline bool discretise(Layers& L, Topo& T, Segs& S, CellIn& C, float&
   {
     float depseg = 0.0f, depths = 0.0f, depthl = L.THICK[1];
     int K = 1;
+    for (int k = 0; k < 23; ++k) { S.LS1[k] = 0; S.LS2[k] = 0; }
+    S.LS1[1] = 1;
     const double rc1 = L.RC[1];
     L.RC[1] = L.RC[1] * (double)CORECT;
     for (int J = 1; J <= 7; ++J) {
       float ul = 0.f, wp = 0.f, fc = 0.f, con = 0.f, rs = 0.f, lam = 0.f, sw = 0.f, rcs = 0.f, bub = 0.f, sub = 0.f;
       if (J == 5) L.RC[1] = rc1;
-      if (depseg >= depthl) { K = K + 1; depthl = depthl + L.THICK[K]; }
+      if (depseg >= depthl) { K = K + 1; S.LS1[K] = J; depthl = depthl + L.THICK[K]; }
       depths = depths + S.STHICK[J];
       for (;;) {
         S.LSEG[J] = L.LAYER[K];
         const bool last = (depths <= depthl) || (K >= 20);
         const float dseg = last ? (depths - depseg) : (depthl - depseg);
+        if (dseg > 0.0001f) S.LS2[K] = J;
         ul = L.PORO[K] * dseg + ul;
         fc = L.FC[K] * dseg + fc;
         wp = L.WP[K] * dseg + wp;
@@ -302,12 +306,20 @@ __device__ inline bool discretise(Layers& L, Topo& T, Segs& S, CellIn& C, float&
         if (last) { depseg = depths; break; }
         depseg = depthl;
         K = K + 1;
+        S.LS1[K] = J;
         depthl = depthl + L.THICK[K];
       }
       S.UL[J] = ul; S.FCUL[J] = fc; S.WPUL[J] = wp; S.CONUL[J] = con; S.BUBUL[J] = bub; S.RCULS[J] = rcs;
       S.RSUL[J] = rs; S.XLAMBU[J] = lam; S.SUBINS[J] = sub; S.SWUL[J] = sw;
     }
     L.RC[1] = rc1;
+  }
+  {
+    int K = S.LAYSEG2[7];
+    for (int J = 8; J <= NS; ++J) {
+      if (S.LAYSEG2[J] != K) { K = S.LAYSEG2[J]; S.LS1[K] = J; }
+      S.LS2[K] = J;
+    }
   }
   for (int J = 8; J <= NS; ++J) {                                      // F:1997-2022
     const int a = S.LAYSEG1[J], b = S.LAYSEG2[J];
@@ -706,6 +718,43 @@ help_setup_kernel(BatchDev B, Image img, const int32_t* __restrict__ perm, uint3
       const int plain = (img.PI(Q_IBAR, N, slot) == 0 && !any && flg == 0 && img.PF(P_SUBLIN, N, slot) == 0.0f) ? 2 : 0;
       img.PI(Q_SUBIN, N, slot) = any | plain;
       e2 += S.NSEGn[N];
+    }
+  }
+  // ---- recirculation plan (RECIRC, F:5311-5440): which segments receive the recirculated share
+  // of which layer, and with what weight -- geometry only, so it is laid out once ---------------
+  {
+    for (int J = 1; J <= img.segcap; ++J) { img.SI2(J, slot) = 0; img.SF(S_RCW, J, slot) = 0.f; }
+    for (int N = 1; N <= 6; ++N) {
+      int t = 0;
+      if (N <= 5 && T.LD[N] != 0 && L.RECIR[T.LD[N]] > 0.0f) t = L.LAYR[T.LD[N]];
+      img.PI(Q_RCRT, N, slot) = t;
+    }
+    for (int K = 1; K <= L.LAY; ++K) {
+      if (LRIN[K] != 1) continue;
+      const int a = S.LS1[K], b = S.LS2[K];
+      if (a < 1 || b < a || b > S.NSEG) continue;
+      auto put = [&](int J, int mode, float w) { img.SI2(J, slot) = mode | (K << 8); img.SF(S_RCW, J, slot) = w; };
+      if (a > 7) { for (int J = a; J <= b; ++J) put(J, 1, L.THICK[K]); }
+      else if (K == 1) {
+        float RCRF = 0.0f;
+        for (int Lx = a; Lx <= b; ++Lx) {
+          if (Lx < b) { put(Lx, 1, L.THICK[K]); RCRF = (float)((double)RCRF + ((double)S.STHICK[Lx] / (double)L.THICK[K])); }
+          else put(Lx, 2, 1.0f - RCRF);
+        }
+      } else if (a == b) put(a, 3, 0.f);
+      else {
+        float TKM1 = 0.0f;
+        for (int M = 1; M <= K - 1; ++M) TKM1 = TKM1 + L.THICK[M];
+        float TJM1 = 0.0f;
+        if (a > 1) for (int M = 1; M <= a - 1; ++M) TJM1 = (float)((double)TJM1 + (double)S.STHICK[M]);
+        const float DSEG = TKM1 - TJM1;
+        float RCRF = (float)(((double)S.STHICK[a] - (double)DSEG) / (double)L.THICK[K]);
+        put(a, 2, RCRF);
+        for (int Lx = a + 1; Lx <= b; ++Lx) {
+          if (Lx < b) { put(Lx, 1, L.THICK[K]); RCRF = (float)((double)RCRF + ((double)S.STHICK[Lx] / (double)L.THICK[K])); }
+          else put(Lx, 2, 1.0f - RCRF);
+        }
+      }
     }
   }
   const int hemi = (C.ULAT >= 0.0f) ? 0 : 1;

@@ -239,7 +239,7 @@ __device__ __noinline__ double lateral_rate(const Image& img, int64_t s, int NSE
 // Per-segment constants come from the routing records (help_image.h): one pointer pair walks
 // down the profile, every constant is a load at a compile-time offset.
 struct ProfC {
-  int n, NSEGB, NSEGE, NSEG, nstep, ibar, lat, subin;
+  int n, NSEGB, NSEGE, NSEG, nstep, ibar, lat, subin, rcr;   // rcr: the cell recirculates drainage (DRCRS may be non-zero)
   float drculs, dthics, slope, xleng, sublin;
   FmlC fml;
   LatC latc;
@@ -253,6 +253,7 @@ template <int MAXSEG>
 struct SegState {
   double2 SB[MAXSEG + 2];
   double DRIN[MAXSEG + 3];
+  double DRCRS[MAXSEG + 2];   // recirculated drainage entering segment j, in/day (RECIRC); touched only by cells that recirculate
 };
 struct RouteOut { double DRN, PRC, HED; float EXTRA; uint32_t flag; };
 #define SWa(j) SS.SB[(j)].x
@@ -278,6 +279,7 @@ __device__ __noinline__ RouteOut route_subprofile(const Image& img, int64_t s, c
   const bool bottom = (NSEGE == NSEG);
   const bool liner = !(IBAR == 0 || IBAR == 3);
   const bool has_sub = PLAIN ? false : ((P.subin & 1) != 0);
+  const bool has_rcr = PLAIN ? false : (P.rcr != 0);
   const char* const p0 = img.rec_p(s) + (int64_t)(NSEGB - 1) * kRecBytes;
   const char* const pL = p0 + (int64_t)(NSEGL - NSEGB) * kRecBytes;
   const double LOWFC_L = rec_tail(pL).lowfc;            // SWLIM = FC occurs at segment NSEGL only
@@ -332,6 +334,7 @@ __device__ __noinline__ RouteOut route_subprofile(const Image& img, int64_t s, c
       const double span = ul - rs;
       const double Ej = (J <= 7) ? Ed[J] : 0.0;
       const double DSUBj = has_sub ? (double)rec_tail(p).subin * DT : 0.0;
+      const double DRCRj = has_rcr ? SS.DRCRS[J] * DT : 0.0;            // DRCR(J) (F:4195)
       // lower storage limit SWLIM and the drainage LOW at that limit; kind: 0 capillary
       // equilibrium with the segment below, 1 wilting point, 2 field capacity, 3 porosity
       // (frozen soil)
@@ -378,7 +381,7 @@ __device__ __noinline__ RouteOut route_subprofile(const Image& img, int64_t s, c
 #ifdef HELP_DBG_SWEEP
       HELP_DBG_SWEEP
 #endif
-      double DRNMAX = PLAIN ? (base + drin - Ej - swl) : (base + drin + DSUBj - Ej - swl);
+      double DRNMAX = PLAIN ? (base + drin - Ej - swl) : (base + drin + DSUBj + DRCRj - Ej - swl);
       if (J == NSEGL) {
         if (bottom) {
           if (IBAR == 3) DRNMAX = 0.0;
@@ -414,7 +417,7 @@ __device__ __noinline__ RouteOut route_subprofile(const Image& img, int64_t s, c
       double out;
       if (LOW > DRNMAX) out = DRNMAX;
       else {
-        double SWMAX = PLAIN ? (base + drin - Ej) : (base + DSUBj + drin - Ej);
+        double SWMAX = PLAIN ? (base + drin - Ej) : (base + DSUBj + DRCRj + drin - Ej);
         if (add_sub) SWMAX = SWMAX + DSUBE;
         if (SWMAX > ul) SWMAX = ul;
         if (SWMAX <= swl) out = 0.0;
@@ -426,14 +429,14 @@ __device__ __noinline__ RouteOut route_subprofile(const Image& img, int64_t s, c
           if (SWMIN < swl) SWMIN = swl;
           LOW = kdt * r8_pow(fdiv_by(SWMIN - rs, span, rspan), C);
           if (LOW > DRNMAX) LOW = DRNMAX;
-          SWMAX = PLAIN ? (base + drin - Ej - LOW) : (base + DSUBj + drin - Ej - LOW);
+          SWMAX = PLAIN ? (base + drin - Ej - LOW) : (base + DSUBj + DRCRj + drin - Ej - LOW);
           if (add_sub) SWMAX = SWMAX + DSUBE;
           if (SWMAX > ul) SWMAX = ul;
           if (SWMAX <= SWMIN) out = DRNMAX;
           else {
             // Newton on f(x) = A - B x^C - 2x (F:4461-4488); B = K dt (1/(ul-rs))^C is a
             // constant of the segment (set-up kernel).  x^C and x^(C-1) share one logarithm.
-            double An = PLAIN ? (2.0 * (swj - rs) + balj + drin - Ej) : (2.0 * (swj - rs) + balj + drin + DSUBj - Ej);
+            double An = PLAIN ? (2.0 * (swj - rs) + balj + drin - Ej) : (2.0 * (swj - rs) + balj + drin + DSUBj + DRCRj - Ej);
             if (add_sub) An = An + (2.0 * DSUBE);
             const double Bc = Ev.x;
             const double TOLER = 0.003 * span;
@@ -456,7 +459,7 @@ __device__ __noinline__ RouteOut route_subprofile(const Image& img, int64_t s, c
             if (ITER > 100) flag |= kFlagNonConv;
             if (X0 > SWMAX) X0 = SWMAX;
             if (X0 < SWMIN) X0 = SWMIN;
-            out = PLAIN ? (2.0 * (swj - X0) + balj + drin - Ej) : (2.0 * (swj - X0) + balj + drin + DSUBj - Ej);
+            out = PLAIN ? (2.0 * (swj - X0) + balj + drin - Ej) : (2.0 * (swj - X0) + balj + drin + DRCRj + DSUBj - Ej);
             if (bottom && IBAR > 3) out = out + DSUBE;
           }
         }
@@ -477,7 +480,7 @@ __device__ __noinline__ RouteOut route_subprofile(const Image& img, int64_t s, c
           const float sw = (float)fdiv_by(base - rs, span, rspan);
           const float TRATIO = (float)(th / th1);
           const double En = (J + 1 <= 7) ? Ed[J + 1] : 0.0;
-          double DRMX = ul1 - sw1 - (bal1 / 2.0) + kdt1 + En - sub1 * DT;
+          double DRMX = ul1 - sw1 - (bal1 / 2.0) + kdt1 + En - sub1 * DT - (has_rcr ? SS.DRCRS[J + 1] * DT : 0.0);
           if (DRMX > DRNMAX) DRMX = DRNMAX;
           double DRNMX = kdt1 * (double)(1.0f + (sw * TRATIO));
           if (DRNMX > DRMX) DRNMX = DRMX;
@@ -511,7 +514,7 @@ __device__ __noinline__ RouteOut route_subprofile(const Image& img, int64_t s, c
         const double swk_n = sbn.x, balk_n = sbn.y;
         const double ul = (double)ulf;
         const double Ek = (Kk <= 7) ? Ed[Kk] : 0.0;
-        double BALT = PLAIN ? (din - dnext - Ek) : (din + sub - dnext - Ek);
+        double BALT = PLAIN ? (din - dnext - Ek) : (din + sub + (has_rcr ? SS.DRCRS[Kk] * DT : 0.0) - dnext - Ek);
         if (Kk == NSEGL && IBAR > 3) BALT = BALT + DSUBE;
         const double DSW = swk + ((balk + BALT) / 2.0);
         const double S = DSW + EXC + (BALT / 2.0);
@@ -625,6 +628,8 @@ __global__ void __launch_bounds__(THREADS) __maxnreg__(REGS) help_sim_kernel(Sim
   ProfC PR[7];
   int LDn[7] = {0, 0, 0, 0, 0, 0, 0};
   float RECIR[7];
+  int RCRT[7] = {0, -1, -1, -1, -1, -1, -1};      // layer the recirculated drainage of subprofile n goes to (0 = none)
+  const bool has_rcr = (flag & kFlagRecirc) != 0;
   {
     int e = 0;
     for (int N = 1; N <= 6; ++N) {
@@ -632,6 +637,7 @@ __global__ void __launch_bounds__(THREADS) __maxnreg__(REGS) help_sim_kernel(Sim
       const int ns = img.PI(Q_NSEGN, N, s);
       p.n = N; p.NSEGB = e + 1; p.NSEGE = e + ns; p.NSEG = NSEG;
       p.nstep = img.PI(Q_NSTEP, N, s); p.ibar = img.PI(Q_IBAR, N, s); p.lat = img.PI(Q_LAT, N, s); p.subin = img.PI(Q_SUBIN, N, s);
+      p.rcr = (flag & kFlagRecirc) ? 1 : 0;
       p.drculs = img.PF(P_DRCULS, N, s); p.dthics = img.PF(P_DTHICS, N, s);
       p.slope = img.PF(P_SLOPE, N, s); p.xleng = img.PF(P_XLENG, N, s); p.sublin = img.PF(P_SUBLIN, N, s);
       p.fml.lcase = img.PI(Q_LCASE, N, s); p.fml.lpq = img.PI(Q_LPQ, N, s); p.fml.ltype = img.PI(Q_LTYPE, N, s);
@@ -644,6 +650,7 @@ __global__ void __launch_bounds__(THREADS) __maxnreg__(REGS) help_sim_kernel(Sim
         if (p.lat == 1) p.latc = lateral_consts(p.slope, p.xleng);
       }
       RECIR[N] = img.PF(P_RECIR, N, s);
+      RCRT[N] = img.PI(Q_RCRT, N, s);
       LDn[N] = (N <= 5 && ns > 0) ? img.PI(Q_LD, N, s) : 0;
       e += ns;
     }
@@ -654,6 +661,7 @@ __global__ void __launch_bounds__(THREADS) __maxnreg__(REGS) help_sim_kernel(Sim
   // (profiles/r1_notes.md).
   SegState<MAXSEG> SS;
   for (int J = 1; J <= NSEG; ++J) { SWa(J) = (double)img.SF(S_SW0, J, s); BALa(J) = 0.0; }
+  if (has_rcr) for (int J = 0; J < MAXSEG + 2; ++J) SS.DRCRS[J] = 0.0;
   SWa(0) = 0.0; BALa(0) = 0.0; SWa(NSEG + 1) = 0.0; BALa(NSEG + 1) = 0.0;
   Surf U;
   U.RUN = 0.f; U.ES1T = 0.f; U.TS2 = 0.f; U.ADDRUN = 0.f;
@@ -1244,6 +1252,7 @@ __global__ void __launch_bounds__(THREADS) __maxnreg__(REGS) help_sim_kernel(Sim
         // ---------------- subsurface routing, subprofile 1 (F:631-693) ----------------
         double DRN[7], PRC[7];
         double HEDd[4] = {0.0, 0.0, 0.0, 0.0}, DRNd[4] = {0.0, 0.0, 0.0, 0.0};   // daily channel only
+        double RCRn[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};                          // RCR(n): today's recirculated drainage
         U.ADDRUN = 0.0f;
 #ifdef HELP_DBG_PRE
         HELP_DBG_PRE
@@ -1279,6 +1288,7 @@ __global__ void __launch_bounds__(THREADS) __maxnreg__(REGS) help_sim_kernel(Sim
           const double RCR = (double)RECIR[1] * DRN[1] / (double)100.0f;
           DRN[1] = DRN[1] - RCR;
           DRNd[1] = DRN[1] + RCR;
+          RCRn[1] = RCR;
         }
         DRNM[1] = (float)((double)DRNM[1] + DRN[1]);
         PRCM[1] = (float)((double)PRCM[1] + PRC[1]);
@@ -1297,10 +1307,25 @@ __global__ void __launch_bounds__(THREADS) __maxnreg__(REGS) help_sim_kernel(Sim
               const double RCR = (double)RECIR[N] * DRN[N] / (double)100.0f;
               DRN[N] = DRN[N] - RCR;
               if (N <= 3) DRNd[N] = DRN[N] + RCR;
+              RCRn[N] = RCR;
             }
             DRNM[N] = (float)((double)DRNM[N] + DRN[N]);
           }
           PRCM[N] = (float)((double)PRCM[N] + PRC[N]);
+        }
+        // ---------------- RECIRC (F:5311-5440): today's recirculated drainage becomes tomorrow's
+        // source term DRCRS(J) of the segments of the receiving layers ----------------
+        if (has_rcr) {
+          for (int J = 1; J <= NSEG; ++J) {
+            const int plan = img.SI2(J, s);
+            const int mode = plan & 0xff, K = plan >> 8;
+            if (mode == 0) continue;
+            double RCRI = 0.0;
+            for (int N = 1; N <= 5; ++N) if (RCRT[N] == K) RCRI = RCRI + RCRn[N];
+            const float w = img.SF(S_RCW, J, s);
+            SS.DRCRS[J] = (mode == 1) ? RCRI * (double)img.SF(S_THICK, J, s) / (double)w
+                        : (mode == 2) ? RCRI * (double)w : RCRI;
+          }
         }
 #ifdef HELP_DBG_DAY
         HELP_DBG_DAY

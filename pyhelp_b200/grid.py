@@ -96,7 +96,7 @@ def batch_from_grid(grid: dict, years_of_day, precip, airtemp, solrad, node_p, n
     lay_type{i}, thick{i}, poro{i}, fc{i}, wp{i}, ksat{i}, dist_dr{i}, slope{i}).
     ``precip``/``airtemp``/``solrad``: [day][node] tables in mm, deg C, MJ/m2/day.
     ``extra_layers``: optional per-layer design fields PyHELP's formatter leaves blank
-    (phole{i}, defec{i}, ipq{i}, trans{i}, recir{i}, subin{i}) for landfill designs.
+    (phole{i}, defec{i}, ipq{i}, trans{i}, recir{i}, layr{i}, subin{i}) for landfill designs.
     Cells PyHELP would skip (nlayer == 0 or a -9999 layer field,
     preprocessing.py:32-35,150-153) must be removed by the caller (`runnable_cells`).
     """
@@ -155,6 +155,7 @@ def batch_from_grid(grid: dict, years_of_day, precip, airtemp, solrad, node_p, n
             layer_f32[N.HL_RECIR, j] = col("recir")
             layer_f32[N.HL_SUBIN, j] = col("subin")
             layer_i32[N.HL_IPQ, j] = col("ipq").astype(np.int32)
+            layer_i32[N.HL_LAYR, j] = col("layr").astype(np.int32)
             if f"thick_exact{s}" in ex:          # landfill liners are thinner than MINTHICK
                 layer_f32[N.HL_THICK, j] = np.where(on, np.asarray(ex[f"thick_exact{s}"], dtype=float), 0)
     years, pre = weather_to_nodes(years_of_day, np.asarray(precip, float), 1)

@@ -146,11 +146,13 @@ def grid_mixed(n: int, seed: int = 2):
     return g
 
 
-def grid_landfill(n: int, seed: int = 3):
+def grid_landfill(n: int, seed: int = 3, recirc: bool = False):
     """BASELINE config 4: cover = topsoil / lateral drain / geomembrane / clay, half of the
     cells with a second liner system underneath (waste / drain / geomembrane / clay).
     Returns (grid, extra_layers) -- the extra design fields PyHELP's formatter leaves
-    blank (pinholes, defects, placement quality)."""
+    blank (pinholes, defects, placement quality).  ``recirc``: the lateral-drain layers send
+    10-60 % of their drainage back into a soil layer above (leachate recirculation, D10 fields
+    RECIR / LAYR, reference ``HELP3O.FOR:5311-5440``)."""
     rng = np.random.default_rng(seed)
     g = _base_grid(n, rng)
     two = rng.random(n) < 0.5
@@ -178,6 +180,13 @@ def grid_landfill(n: int, seed: int = 3):
             ex["phole" + s] = np.where(on, rng.integers(0, 3, n), 0).astype(float)
             ex["defec" + s] = np.where(on, rng.integers(0, 11, n), 0).astype(float)
             ex["ipq" + s] = np.where(on, rng.integers(2, 6, n), 0)
+    if recirc:
+        rr = np.random.default_rng(seed + 77)
+        for j, targets in ((2, (1,)), (6, (1, 5))):              # drain layer -> layer(s) it may recirculate to
+            s = str(j)
+            on = nl >= j
+            ex["recir" + s] = np.where(on, rr.integers(10, 61, n), 0).astype(float)
+            ex["layr" + s] = np.where(on, rr.choice(targets, n), 0).astype(int)
     return g, ex
 
 
@@ -248,7 +257,8 @@ def format_d10(g: dict, i: int, sf_cn=1.0, ex: dict | None = None) -> list:
                 return fmt.format(ex[name + s][i])
             return " " * blank_w
         out.append("{0:>7.0f}".format(float(g["dist_dr" + s][i])) + "{0:>6.2f}".format(float(g["slope" + s][i])) +
-                   "{0:>6}".format("") + "{0:>3}".format(0) + "{0:>13}".format("") +
+                   opt("recir", "{0:>6.0f}", 6) + ("{0:>3d}".format(int(ex["layr" + s][i])) if "layr" + s in ex else "{0:>3}".format(0)) +
+                   "{0:>13}".format("") +
                    opt("phole", "{0:>7.0f}", 7) + opt("defec", "{0:>7.0f}", 7) + opt("ipq", "{0:>2d}", 2) +
                    "{0:>14}".format(""))
     return out

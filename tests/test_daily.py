@@ -48,11 +48,12 @@ def test_rcra_daily_table_on_the_gpu():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("family", ["mixed", "landfill"])
+@pytest.mark.parametrize("family", ["mixed", "landfill", "recirc"])
 def test_liner_profiles_daily_bits(tmp_path, family):
     """barrier soil, geomembrane, lateral drainage: head / drainage / leakage columns too"""
     n, ny, nn = 24, 2, 2
-    res = {"mixed": synth.grid_mixed, "landfill": synth.grid_landfill}[family](n, seed=17)
+    res = {"mixed": synth.grid_mixed, "landfill": synth.grid_landfill,
+           "recirc": lambda n, seed: synth.grid_landfill(n, seed=seed, recirc=True)}[family](n, seed=17)
     g, ex = res if isinstance(res, tuple) else (res, None)
     wx = synth.synth_weather(nn, 2001, ny, seed=2)
     files = synth.write_weather_files(str(tmp_path), wx)

@@ -12,9 +12,10 @@ from pyhelp_b200 import inputs, synth
 from pyhelp_b200 import _native as N
 
 
-@pytest.mark.parametrize("family", ["natural3", "mixed", "landfill"])
+@pytest.mark.parametrize("family", ["natural3", "mixed", "landfill", "recirc"])
 def test_vectorised_packer_equals_text_round_trip(tmp_path, family):
-    maker = {"natural3": synth.grid_natural_3layer, "mixed": synth.grid_mixed, "landfill": synth.grid_landfill}[family]
+    maker = {"natural3": synth.grid_natural_3layer, "mixed": synth.grid_mixed, "landfill": synth.grid_landfill,
+             "recirc": lambda n, seed: synth.grid_landfill(n, seed=seed, recirc=True)}[family]
     res = maker(50, seed=13)
     g, ex = res if isinstance(res, tuple) else (res, None)
     ny, nn = 2, 5
