@@ -15,7 +15,9 @@
 //                   liner leakage (Darcy or geomembrane), lateral drainage,
 //                   unsaturated drainage segment by segment (Newton), upward
 //                   redistribution of super-saturation                   F:4133-4734, 4870-5304
+//   recirculation of lateral drainage into a layer above (RECIRC)      F:5311-5440
 //   the day/year driver, monthly accounting, spin-up restart            F:490-997
+//   optional daily channel (OUTDAY columns) for selected cells          F:5984-6029
 //   monthly report value semantics (x25.4, F7.3, row->key mapping)      F:6415-6600,
 //                                                    pyhelp/processing.py:64-147
 //
@@ -25,10 +27,15 @@
 // QSTARN F:4723; QPHOLE/QDEFEC/RSQR/DENOM F:4896-4897).  The file is compiled
 // with -fmad=false: every operation rounds once, like gfortran's SSE2 code.
 //
-// State held per thread between days:
-//   double SW[j]   segment storage (DSWUL == SWULY between sub-steps)
-//   double BAL[j]  storage change of the last sub-step (BALT == BALY == DCHG at day end)
+// State held per thread between days (SegState):
+//   SB[j].x  segment storage (DSWUL == SWULY between sub-steps)
+//   SB[j].y  storage change of the last sub-step (BALT == BALY == DCHG at day end)
+//   DRCRS[j] recirculated drainage entering the segment (cells that recirculate only)
 // plus ~45 float/int scalars (snow pack, frozen-soil window, vegetation, ...).
+//
+// The per-segment constants of the routing loop come from the tile-major routing records
+// (help_image.h); what shaped the loop -- and what was tried and rejected -- is in DESIGN.md
+// section 3 and profiles/r1_notes.md.
 #pragma once
 #include "help_image.h"
 
