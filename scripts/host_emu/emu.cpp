@@ -1,6 +1,9 @@
 // DEVELOPER DEBUGGING AID (see cuda_shim.h).  Runs help_setup_kernel + help_sim_kernel
 // on the CPU, thread by thread.  Build: g++ -O1 -g -ffp-contract=off -shared -fPIC emu.cpp -o libemu.so
 #include "cuda_shim.h"
+#ifndef EMU_MAXSEG
+#define EMU_MAXSEG 67   // template tier of the emulated instantiation (16: the natural-soil tier with its tight arrays)
+#endif
 #ifndef EMU_REGS
 #define EMU_REGS 128     // register budget of the emulated instantiation (>= 96: carried look-ahead; below: no-carry loop)
 #endif
@@ -47,9 +50,9 @@ extern "C" int emu_run(const help_b200_batch* b, float* monthly, float* yearly, 
   A.monthly = monthly; A.yearly = yearly; A.raw = raw; A.flags = flags; std::vector<int32_t> drow(n); for (int64_t c = 0; c < n; ++c) drow[c] = (int32_t)c;
   A.daily = g_daily; A.daily_row = g_daily ? drow.data() : nullptr; A.daily_days = g_daily_days;
 #ifdef HELP_DBG_CAPMEMO
-  for (int64_t c = 0; c < n; ++c) { blockIdx.x = (unsigned)c; memo2_newcell(); help_sim_kernel<67, 128, EMU_REGS>(A); }
+  for (int64_t c = 0; c < n; ++c) { blockIdx.x = (unsigned)c; memo2_newcell(); help_sim_kernel<EMU_MAXSEG, 128, EMU_REGS>(A); }
 #else
-  for (int64_t c = 0; c < n; ++c) { blockIdx.x = (unsigned)c; help_sim_kernel<67, 128, EMU_REGS>(A); }
+  for (int64_t c = 0; c < n; ++c) { blockIdx.x = (unsigned)c; help_sim_kernel<EMU_MAXSEG, 128, EMU_REGS>(A); }
 #endif
   return 0;
 }
