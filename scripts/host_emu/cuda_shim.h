@@ -92,3 +92,28 @@ static MemoStat g_memo[4096];
 #define HELP_DBG_PRE2 { MemoStat& M = g_memo[s]; M.pre.push_back(ra == M.prelsw[J]); M.pre.push_back(rb == M.prelsw[J + 1]); M.prelsw[J] = ra; M.prelsw[J + 1] = rb; }
 #define HELP_DBG_SWEEP { MemoStat& M = g_memo[s]; bool hit = (base == M.pb[J] && drin == M.pd[J] && Ej == M.pe[J] && swl == M.ps[J]); M.swp.push_back(hit); M.pb[J] = base; M.pd[J] = drin; M.pe[J] = Ej; M.ps[J] = swl; }
 #endif
+
+#ifdef HELP_EMU_STAGE   // per-cell stream of (capillary limit?, single powers, shared-base pairs) per segment iteration
+#define HELP_R4_OVERRIDE
+#include <vector>
+#include "../../pyhelp_b200/csrc/help_math.h"
+static int g_np = 0, g_nsb = 0;
+static std::vector<unsigned char> g_stage[8192];
+namespace helpb200 {
+using helpmath::r4_exp; using helpmath::r4_log; using helpmath::r4_log10; using helpmath::r4_sin;
+using helpmath::r4_cos; using helpmath::r4_tan; using helpmath::r4_acos; using helpmath::r4_pow;
+using helpmath::r4_sqrt; using helpmath::r4_pow8; using helpmath::r4_pow7; using helpmath::r4_pow4;
+static inline double r8_log(double x) { return helpmath::det_log(x); }
+static inline void r8_log_pair(double x, double& hi, double& lo) { helpmath::det_log_pair(x, hi, lo); }
+static inline double r8_pow_logbase(double x, double hi, double lo, double y) { return helpmath::det_pow_logbase(x, hi, lo, y); }
+static inline double r8_atan(double x) { return helpmath::det_atan(x); }
+static inline double r8_sin(double x) { return helpmath::det_sin(x); }
+static inline double r8_cos(double x) { return helpmath::det_cos(x); }
+static inline double r8_sqrt(double x) { return helpmath::hm_sqrt(x); }
+static inline double r8_pow(double x, double y) { g_np++; return helpmath::det_pow(x, y); }
+static inline void r8_pow2(double x0, double y0, double x1, double y1, double& r0, double& r1) { g_np += 2; auto R = helpmath::det_pow2(x0, y0, x1, y1); r0 = R.a; r1 = R.b; }
+static inline void r8_pow_sb(double x, double y0, double y1, double& r0, double& r1) { g_nsb++; auto R = helpmath::det_pow_samebase(x, y0, y1); r0 = R.a; r1 = R.b; }
+}
+// at the hook of iteration i: the powers since the previous hook are [HIGH, LOW, Newton of i-1] + [capillary limit of i]
+#define HELP_DBG_SWEEP { auto& V = g_stage[s]; const int cap = (kind == 0) ? 3 : 0; V.push_back((unsigned char)(g_np - cap)); V.push_back((unsigned char)g_nsb); V.push_back((unsigned char)cap); V.push_back((unsigned char)J); g_np = 0; g_nsb = 0; }
+#endif
