@@ -115,5 +115,5 @@ static inline void r8_pow2(double x0, double y0, double x1, double y1, double& r
 static inline void r8_pow_sb(double x, double y0, double y1, double& r0, double& r1) { g_nsb++; auto R = helpmath::det_pow_samebase(x, y0, y1); r0 = R.a; r1 = R.b; }
 }
 // at the hook of iteration i: the powers since the previous hook are [HIGH, LOW, Newton of i-1] + [capillary limit of i]
-#define HELP_DBG_SWEEP { auto& V = g_stage[s]; const int cap = (kind == 0) ? 3 : 0; V.push_back((unsigned char)(g_np - cap)); V.push_back((unsigned char)g_nsb); V.push_back((unsigned char)cap); V.push_back((unsigned char)J); g_np = 0; g_nsb = 0; }
+#define HELP_DBG_SWEEP { auto& V = g_stage[s]; const int cap = (kind == 0) ? 3 : 0; const bool dryj = (kind == 0) && ((base + drin - Ej - wp) <= 0.0); V.push_back((unsigned char)(g_np - cap)); V.push_back((unsigned char)g_nsb); V.push_back((unsigned char)(cap + (dryj ? 1 : 0))); V.push_back((unsigned char)J); g_np = 0; g_nsb = 0; }
 #endif

@@ -38,7 +38,11 @@ for w in range(n // 32):
     A = np.stack(S).astype(np.float64)          # [32, L, 4] = tail single pows (of i-1), tail pairs (of i-1), cap of i, J
     J = A[0, :, 3]
     if not (A[:, :, 3] == J).all(): tot["skipped"] += 1; continue
-    cap = A[:, :, 2]
+    capraw = A[:, :, 2]
+    dry = capraw == 4; cap = np.where(capraw >= 3, 3.0, 0.0)
+    need = (cap > 0) & ~dry
+    tot["cap_lane"] = tot.get("cap_lane", 0) + (cap > 0).sum(); tot["cap_lane_dry"] = tot.get("cap_lane_dry", 0) + dry.sum()
+    anyc = (cap > 0).any(0); tot["cap_warp"] = tot.get("cap_warp", 0) + anyc.sum(); tot["cap_warp_skip"] = tot.get("cap_warp_skip", 0) + (anyc & ~need.any(0)).sum()
     hl = np.roll(A[:, :, 0], -1, axis=1); nw = np.roll(A[:, :, 1], -1, axis=1)
     hl[:, -1] = 0; nw[:, -1] = 0
     lane = cap + hl + SB * nw
@@ -53,3 +57,5 @@ print("pow passes per warp, shared-base pair = %.1f pow:" % SB)
 print("  today (stage by stage)            %.4g   lane efficiency %.1f %%" % (tot["cur"], 100 * tot["lanepow"] / (32 * tot["cur"])))
 print("  state machine, sync per segment   %.4g   (%.1f %% of today)  lane efficiency %.1f %%" % (tot["seg"], 100 * tot["seg"] / tot["cur"], 100 * tot["lanepow"] / (32 * tot["seg"])))
 print("  state machine, sync per sub-step  %.4g   (%.1f %% of today)  lane efficiency %.1f %%" % (tot["sub"], 100 * tot["sub"] / tot["cur"], 100 * tot["lanepow"] / (32 * tot["sub"])))
+print("capillary limits: lane evaluations %d, of which storage at/below WP (skippable) %.1f %%; warp evaluations %d, all needing lanes skippable %.1f %%" % (
+    tot["cap_lane"], 100.0 * tot["cap_lane_dry"] / tot["cap_lane"], tot["cap_warp"], 100.0 * tot["cap_warp_skip"] / tot["cap_warp"]))
