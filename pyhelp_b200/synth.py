@@ -114,6 +114,48 @@ def grid_natural_3layer(n: int, seed: int = 1):
     return g
 
 
+def grid_example(n: int = 17_178, seed: int = 20260101):
+    """BASELINE config 1 stand-in: the reference's example grid
+    (``example/input_grid.csv``) is a missing blob in the checkout, so this is a schema-exact
+    synthetic grid (columns of ``docs/data.rst:122-188``) with the value ranges of
+    ``docs/img/grid_input_data.png``: cells on a 250 m lattice over lat 45.78-46.2, lon -74.5..-74.0
+    (the footprint of the example weather nodes), 1-3 type-1 layers, some cells not runnable
+    (``run == 0``, ``nlayer == 0``) and a ``Bassin`` column like the example's sub-basin selector."""
+    rng = np.random.default_rng(seed)
+    ncol = int(np.ceil(np.sqrt(n * 1.19)))              # lattice aspect of the footprint
+    nrow = int(np.ceil(n / ncol))
+    iy, ix = np.divmod(np.arange(n), ncol)
+    lat = 45.78 + (46.2 - 45.78) * iy / max(nrow - 1, 1)
+    lon = -74.5 + 0.5 * ix / max(ncol - 1, 1)
+    g = {
+        "cid": np.array([str(i) for i in range(n)]),
+        "lat_dd": np.round(lat, 5), "lon_dd": np.round(lon, 5),
+        "wind": np.full(n, 10.0),
+        "hum1": np.full(n, 67.9), "hum2": np.full(n, 65.5), "hum3": np.full(n, 74.0), "hum4": np.full(n, 75.7),
+        "growth_start": np.full(n, 112), "growth_end": np.full(n, 313),
+        "LAI": rng.choice([0.0, 0.2, 3.5], n, p=[0.1, 0.2, 0.7]),
+        "EZD": rng.choice([10.0, 20.0, 60.0], n, p=[0.2, 0.3, 0.5]),
+        "CN": rng.integers(24, 89, n).astype(float),
+        "context": rng.choice([0, 1, 2, 3], n, p=[0.04, 0.82, 0.10, 0.04]),
+        "Bassin": (rng.random(n) < 0.6).astype(int),
+    }
+    nl = rng.choice([0, 1, 2, 3], n, p=[0.02, 0.28, 0.40, 0.30])
+    g["nlayer"] = nl
+    g["run"] = np.where((g["context"] == 0) | (g["context"] == 3) | (nl == 0), 0, 1)     # water / outside cells do not run
+    for j in (1, 2, 3):
+        s = str(j)
+        on = nl >= j
+        g["lay_type" + s] = np.where(on, 1, 0)
+        g["thick" + s] = np.where(on, rng.integers(20, 301, n), 0).astype(float)
+        g["poro" + s] = np.where(on, np.round(rng.uniform(0.437, 0.473, n), 3), 0)
+        g["fc" + s] = np.where(on, np.round(rng.uniform(0.105, 0.222, n), 3), 0)
+        g["wp" + s] = np.where(on, np.round(rng.uniform(0.047, 0.104, n), 3), 0)
+        g["ksat" + s] = np.where(on, np.round(rng.uniform(5.2e-4, 1.7e-3, n), 14), 0)
+        g["dist_dr" + s] = np.where(on, rng.choice([5.0, 25.0], n), 0)
+        g["slope" + s] = np.where(on, np.round(rng.uniform(0.5, 4.6, n), 2), 0)
+    return g
+
+
 def grid_mixed(n: int, seed: int = 2):
     """BASELINE config 3: 50 % 3-layer natural, 20 % 1-layer, 20 % 1/2/3 (drain over
     barrier soil), 10 % 5-layer 1/1/2/3/1."""
