@@ -293,25 +293,9 @@ static int pick_shape(int64_t n, int device) {
   return 3;
 }
 
-// Lanes per warp that carry a cell.  All cells of a launch take the same time, so a batch that fills
-// its last wave only partly would leave some SMs one block short while the full ones set the run
-// time; spreading the batch over every warp of the wave (e.g. 29 of 32 lanes) evens the SMs out.
-// HELP_B200_LANES overrides (developer A/B runs; 32 = dense warps).
-static int pick_lanes(int64_t n, int threads_per_sm, int device) {
-  if (const char* f = getenv("HELP_B200_LANES")) { const int v = atoi(f); if (v >= 1 && v <= 32) return v; }
-  int sms = 148;
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-  const int64_t warps_per_wave = (int64_t)sms * (threads_per_sm / 32);
-  const int64_t waves = (n + warps_per_wave * 32 - 1) / (warps_per_wave * 32);
-  const int64_t lanes = (n + waves * warps_per_wave - 1) / (waves * warps_per_wave);
-  return lanes < 1 ? 1 : lanes > 32 ? 32 : (int)lanes;
-}
-
 template <int MAXSEG, int THREADS, int REGS>
-static void launch_sim(SimArgs& A, int64_t n, cudaStream_t st, int device) {
-  A.lanes = pick_lanes(n, (65536 / (REGS * THREADS)) * THREADS, device);
-  const int64_t per_block = (int64_t)A.lanes * (THREADS / 32);
-  help_sim_kernel<MAXSEG, THREADS, REGS><<<(unsigned)((n + per_block - 1) / per_block), THREADS, 0, st>>>(A);
+static void launch_sim(const SimArgs& A, int64_t n, cudaStream_t st) {
+  help_sim_kernel<MAXSEG, THREADS, REGS><<<(unsigned)((n + THREADS - 1) / THREADS), THREADS, 0, st>>>(A);
 }
 
 extern "C" int help_b200_engine_simulate(help_b200_engine* e, void* stream) {
@@ -342,16 +326,16 @@ extern "C" int help_b200_engine_simulate(help_b200_engine* e, void* stream) {
     switch (e->maxseg_t) {
       case 16:
         switch (pick_shape(n, e->device)) {
-          case 0: launch_sim<16, 128, 128>(A, n, st, e->device); break;
-          case 1: launch_sim<16, 128, 96>(A, n, st, e->device); break;
-          case 2: launch_sim<16, 128, 80>(A, n, st, e->device); break;
-          default: launch_sim<16, 128, 64>(A, n, st, e->device); break;
+          case 0: launch_sim<16, 128, 128>(A, n, st); break;
+          case 1: launch_sim<16, 128, 96>(A, n, st); break;
+          case 2: launch_sim<16, 128, 80>(A, n, st); break;
+          default: launch_sim<16, 128, 64>(A, n, st); break;
         }
         break;
 #ifndef HELP_DEV_FAST_BUILD
-      case 25: launch_sim<25, 128, 128>(A, n, st, e->device); break;
-      case 40: launch_sim<40, 128, 128>(A, n, st, e->device); break;
-      default: launch_sim<67, 128, 128>(A, n, st, e->device); break;
+      case 25: launch_sim<25, 128, 128>(A, n, st); break;
+      case 40: launch_sim<40, 128, 128>(A, n, st); break;
+      default: launch_sim<67, 128, 128>(A, n, st); break;
 #else
       default: return fail(HELP_B200_EINVAL, "developer build: MAXSEG 16 only");
 #endif

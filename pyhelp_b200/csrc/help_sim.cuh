@@ -60,8 +60,6 @@ struct SimArgs {
   double* daily;          // [n_selected][daily_days][kDailyCols] or NULL
   const int32_t* daily_row;   // [n] caller cell -> row of `daily`, -1 = not selected
   int64_t daily_days;     // days of the n_years output years
-  int lanes;              // lanes of every warp that carry a cell (1..32): the launcher spreads a batch that does not
-                          // fill its last wave evenly over all warps of the wave instead of leaving SMs short of blocks
 };
 
 // value an F7.3 field takes after the reference's print + float32 re-parse
@@ -589,9 +587,7 @@ struct Surf {      // REAL*4 surface-process state of one cell
 #endif
 template <int MAXSEG, int THREADS, int REGS>
 __global__ void __launch_bounds__(THREADS) __maxnreg__(REGS) help_sim_kernel(SimArgs A) {
-  const int lane = (int)(threadIdx.x & 31u);
-  if (lane >= A.lanes) return;
-  const int64_t s = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * A.lanes + lane;
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= A.n_cells) return;
   const Image& img = A.img;
   const int64_t n = A.n_cells;

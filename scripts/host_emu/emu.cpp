@@ -49,13 +49,11 @@ extern "C" int emu_run(const help_b200_batch* b, float* monthly, float* yearly, 
   SimArgs A; A.img = img; A.pre = pre.data(); A.tmp = tmp.data(); A.rad = rad.data(); A.years = b->years; A.n_years = ny; A.n_cells = n; A.perm = nullptr;
   A.monthly = monthly; A.yearly = yearly; A.raw = raw; A.flags = flags; std::vector<int32_t> drow(n); for (int64_t c = 0; c < n; ++c) drow[c] = (int32_t)c;
   A.daily = g_daily; A.daily_row = g_daily ? drow.data() : nullptr; A.daily_days = g_daily_days;
-  A.lanes = 32; blockDim.x = 32;   // dense warps: thread (c >> 5, c & 31) carries cell c
 #ifdef HELP_DBG_CAPMEMO
-  for (int64_t c = 0; c < n; ++c) { blockIdx.x = (unsigned)(c >> 5); threadIdx.x = (unsigned)(c & 31); memo2_newcell(); help_sim_kernel<EMU_MAXSEG, 128, EMU_REGS>(A); }
+  for (int64_t c = 0; c < n; ++c) { blockIdx.x = (unsigned)c; memo2_newcell(); help_sim_kernel<EMU_MAXSEG, 128, EMU_REGS>(A); }
 #else
-  for (int64_t c = 0; c < n; ++c) { blockIdx.x = (unsigned)(c >> 5); threadIdx.x = (unsigned)(c & 31); help_sim_kernel<EMU_MAXSEG, 128, EMU_REGS>(A); }
+  for (int64_t c = 0; c < n; ++c) { blockIdx.x = (unsigned)c; help_sim_kernel<EMU_MAXSEG, 128, EMU_REGS>(A); }
 #endif
-  blockDim.x = 1; threadIdx.x = 0;
   return 0;
 }
 #ifdef HELP_EMU_COUNT

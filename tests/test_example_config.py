@@ -140,11 +140,18 @@ def test_example_config_end_to_end(tmp_path):
     data = out.data
     names = data["cid"]
     assert names == hm.get_run_cellnames(sel) and 8_000 < len(names) < 11_000
-    assert np.array_equal(data["years"], np.arange(2000, 2011)) and data["idx_nan"] == []
+    assert np.array_equal(data["years"], np.arange(2000, 2011))
+    # the stand-in grid draws fc and wp independently, so a few soils are inconsistent and HELP itself
+    # returns NaN for them (Brooks-Corey set-up, F:1307-1340) -- they exercise the idx_nan bookkeeping
+    nan_idx = data["idx_nan"]
+    assert 0 < len(nan_idx) < 0.01 * len(names)
+    good = np.ones(len(names), bool)
+    good[nan_idx] = False
     idx = np.array([int(c) for c in names])
     assert np.array_equal(data["lat_dd"], g["lat_dd"][idx])
     for k in KEYS:
-        assert data[k].shape == (len(names), 11, 12) and data[k].dtype == np.float64 and np.isfinite(data[k]).all()
+        assert data[k].shape == (len(names), 11, 12) and data[k].dtype == np.float64 and np.isfinite(data[k][good]).all()
+    assert np.isnan(data["rechg"][nan_idx]).any(axis=(1, 2)).all()
     # nearest node per variable (connect_tables, managers.py:307-313)
     for var in ("precip", "airtemp", "solrad"):
         want = nodes_oracle.nearest_nodes(g["lat_dd"][idx], g["lon_dd"][idx], z[var + "_lat"], z[var + "_lon"])
@@ -152,7 +159,7 @@ def test_example_config_end_to_end(tmp_path):
     assert len(set(hm.connect_tables["precip"].values())) >= 20            # the grid spans the node lattice
     # a sample of cells through the oracle, fed by the reference's text formats
     rng = np.random.default_rng(5)
-    pick = np.sort(rng.choice(len(names), 48, replace=False))
+    pick = np.unique(np.concatenate([rng.choice(len(names), 40, replace=False), np.asarray(nan_idx[:8], dtype=np.int64)]))
     yod = z["year"].astype(np.int32)
     files = {}
     for var, ext in (("precip", "D4"), ("airtemp", "D7"), ("solrad", "D13")):
@@ -168,7 +175,8 @@ def test_example_config_end_to_end(tmp_path):
     ref = oracle.run_help_allcells(cp, ncore=1)
     want = post_oracle.post_process_output(ref, g["context"][cells].tolist())
     for k in KEYS:
-        assert np.array_equal(data[k][pick], want[k]), k
+        assert np.array_equal(data[k][pick], want[k], equal_nan=True), k
+    assert [int(pick[i]) for i in want["idx_nan"]] == [i for i in nan_idx if i in set(pick.tolist())]
     # the reductions of pyhelp/output.py on the whole run
     area, cyr = out.calc_area_monthly_avg(), out.calc_cells_yearly_avg()
     want_area, want_cyr = post_oracle.calc_area_monthly_avg(data), post_oracle.calc_cells_yearly_avg(data)
@@ -179,7 +187,7 @@ def test_example_config_end_to_end(tmp_path):
     tot = {k: out.calc_area_yearly_avg()[k].sum() for k in KEYS}
     resid = tot["precip"] - tot["runoff"] - tot["evapo"] - tot["subrun1"] - tot["subrun2"] - tot["rechg"]
     assert abs(resid) < 0.02 * tot["precip"]
-    assert (data["rechg"][np.asarray(g["context"])[idx] == 2] == 0).all()
+    assert (data["rechg"][(np.asarray(g["context"])[idx] == 2) & good] == 0).all()
 
 
 @pytest.mark.gpu
