@@ -461,7 +461,11 @@ __device__ __noinline__ RouteOut route_subprofile(const Image& img, int64_t s, c
               if (fabs(FX0DER) < 1.0e-03) break;
               const double DX = FX0 / FX0DER;
               X0 = X0 - DX;
-              if (fabs(DX) < TOLER) break;
+              // (written as the negated test so that a NaN step leaves the loop too: from there on the
+              // reference only repeats NaN - NaN until its 100th iteration and reports non-convergence,
+              // F:4481-4483 -- same X0, same flag, without the 99 idle iterations that would make one bad
+              // cell hold back its whole batch)
+              if (!(fabs(DX) >= TOLER)) { if (DX != DX) ITER = 101; break; }
             }
             if (ITER > 100) flag |= kFlagNonConv;
             if (X0 > SWMAX) X0 = SWMAX;
