@@ -232,6 +232,40 @@ def grid_landfill(n: int, seed: int = 3, recirc: bool = False):
     return g, ex
 
 
+def grid_deep(n: int, seed: int = 6):
+    """The largest profiles HELP accepts (HELP3O.FOR COMMON blocks: 20 layers, 67 segments): 12, 16
+    or 20 layers, thick ones (3 segments each), natural soil with up to three drain-over-barrier
+    pairs.  Exercises the widest kernel instantiation (segment capacity 67)."""
+    rng = np.random.default_rng(seed)
+    g = _base_grid(n, rng)
+    nl = rng.choice([12, 16, 20], n, p=[0.3, 0.3, 0.4])
+    g["nlayer"] = nl
+    npairs = rng.integers(0, 4, n)                                    # drain/barrier pairs at layers (5,6), (11,12), (17,18)
+    thick_all = rng.random(n) < 0.3                                   # every layer > 36 in: 3 segments each, 67 in all at 20 layers
+    for j in range(1, 21):
+        on = nl >= j
+        _soil_layer(g, j, n, rng, 1, on=on)
+        s = str(j)
+        g["thick" + s] = np.where(on, np.where(thick_all, rng.integers(95, 151, n), rng.integers(20, 151, n)), 0).astype(float)
+        k = {5: 1, 11: 2, 17: 3}.get(j) or {6: 1, 12: 2, 18: 3}.get(j)
+        if k is None:
+            continue
+        pair = on & (nl >= j + (1 if j in (5, 11, 17) else 0)) & (npairs >= k)
+        if j in (5, 11, 17):                                          # lateral-drainage layer
+            g["lay_type" + s] = np.where(pair, 2, g["lay_type" + s])
+            g["thick" + s] = np.where(pair, rng.integers(20, 46, n), g["thick" + s]).astype(float)
+            g["poro" + s] = np.where(pair, 0.417, g["poro" + s]); g["fc" + s] = np.where(pair, 0.045, g["fc" + s])
+            g["wp" + s] = np.where(pair, 0.018, g["wp" + s])
+            g["ksat" + s] = np.where(pair, np.round(10 ** rng.uniform(-2.5, -1.0, n), 14), g["ksat" + s])
+        else:                                                         # barrier soil below it
+            g["lay_type" + s] = np.where(pair, 3, g["lay_type" + s])
+            g["thick" + s] = np.where(pair, rng.integers(30, 91, n), g["thick" + s]).astype(float)
+            g["poro" + s] = np.where(pair, 0.427, g["poro" + s]); g["fc" + s] = np.where(pair, 0.418, g["fc" + s])
+            g["wp" + s] = np.where(pair, 0.367, g["wp" + s])
+            g["ksat" + s] = np.where(pair, np.round(10 ** rng.uniform(-7.0, -6.0, n), 14), g["ksat" + s])
+    return g
+
+
 def assign_nodes(n_cells: int, n_nodes: int, rng=None) -> np.ndarray:
     """Cells in contiguous blocks per weather node (a gridded-weather layout:
     ~n_cells/n_nodes neighbouring cells share a node)."""

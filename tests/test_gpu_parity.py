@@ -55,11 +55,13 @@ def test_rcra_known_answers_and_bits(rcra_dir):
     assert name == "rcra" and np.array_equal(single["rechg"], got["rcra"]["rechg"])
 
 
-@pytest.mark.parametrize("family,n,ny", [("natural3", 160, 3), ("mixed", 160, 3), ("landfill", 96, 3), ("recirc", 96, 3)])
+@pytest.mark.parametrize("family,n,ny", [("natural3", 160, 3), ("mixed", 160, 3), ("landfill", 96, 3), ("recirc", 96, 3),
+                                         ("deep", 96, 2)])
 def test_grid_families_bit_equal(tmp_path, family, n, ny):
-    """text inputs exactly as HelpManager.calc_help_cells hands them over (managers.py:393-428)"""
+    """text inputs exactly as HelpManager.calc_help_cells hands them over (managers.py:393-428);
+    "deep" = the largest profiles HELP accepts (up to 20 layers / 67 segments: the widest kernel tier)"""
     maker = {"natural3": synth.grid_natural_3layer, "mixed": synth.grid_mixed, "landfill": synth.grid_landfill,
-             "recirc": lambda n, seed: synth.grid_landfill(n, seed=seed, recirc=True)}[family]
+             "recirc": lambda n, seed: synth.grid_landfill(n, seed=seed, recirc=True), "deep": synth.grid_deep}[family]
     res = maker(n, seed=21)
     g, ex = res if isinstance(res, tuple) else (res, None)
     nn = 6

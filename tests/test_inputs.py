@@ -12,10 +12,10 @@ from pyhelp_b200 import inputs, synth
 from pyhelp_b200 import _native as N
 
 
-@pytest.mark.parametrize("family", ["natural3", "mixed", "landfill", "recirc"])
+@pytest.mark.parametrize("family", ["natural3", "mixed", "landfill", "recirc", "deep"])
 def test_vectorised_packer_equals_text_round_trip(tmp_path, family):
     maker = {"natural3": synth.grid_natural_3layer, "mixed": synth.grid_mixed, "landfill": synth.grid_landfill,
-             "recirc": lambda n, seed: synth.grid_landfill(n, seed=seed, recirc=True)}[family]
+             "recirc": lambda n, seed: synth.grid_landfill(n, seed=seed, recirc=True), "deep": synth.grid_deep}[family]
     res = maker(50, seed=13)
     g, ex = res if isinstance(res, tuple) else (res, None)
     ny, nn = 2, 5
@@ -70,3 +70,18 @@ def test_errors():
     d = np.char.ljust(np.array(["a", "b", "c"]), 80).astype("S80")
     with pytest.raises(FileNotFoundError):
         inputs.batch_from_cellparams({"x": ("/nonexistent.D4", "/n.D7", "/n.D13", d, d, "o", 0, 1, 0, 0, 1, 32.0)})
+
+
+def test_deep_family_reaches_the_layer_limit():
+    """20 layers is what the reference's COMMON blocks hold (and include/help_b200.h HELP_B200_MAX_LAYERS)."""
+    g = synth.grid_deep(200, seed=6)
+    assert int(g["nlayer"].max()) == 20
+    wx = synth.synth_weather(2, 2001, 1, seed=5)
+    node = synth.assign_nodes(200, 2)
+    b = G.batch_from_grid(g, wx["years_of_day"], wx["precip"], wx["airtemp"], wx["solrad"], node, node, node)
+    assert b.max_layers == 20 and b.layer_f32.shape[1] == 20
+    types = np.stack([g[f"lay_type{j}"] for j in range(1, 21)])
+    assert (types == 2).any() and (types == 3).any()
+    # a barrier-soil layer always has its lateral-drainage layer directly above
+    jj, cc = np.nonzero(types == 3)
+    assert (types[jj - 1, cc] == 2).all()
