@@ -137,6 +137,17 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def operative_limits():
+    """FP64-pipe / issue / lane utilisation of the simulation kernel from the committed ncu capture
+    (profiles/traffic.json): the counters that bound this kernel, reported next to the HBM fraction
+    the contract asks for.  Profile-derived, not measured in this run."""
+    p = osp.join(ROOT, "profiles", "traffic.json")
+    try:
+        return json.load(open(p)).get("operative_limits")
+    except Exception:
+        return None
+
+
 def measured_traffic():
     """dram bytes per launch of the simulation kernel from the committed ncu capture of this
     workload (profiles/traffic.json, written by scripts/ncu_summary.py), else None."""
@@ -324,7 +335,8 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": measured_traffic(), "kernel": "help_sim_kernel", "kernel_ms": k_ms,
                          "algorithmic_bytes_per_launch": alg, "peak_source": peak_src,
-                         "note": "path is FP64-compute bound (DESIGN.md): the HBM fraction is small by construction"},
+                         "note": "path is FP64-compute bound (DESIGN.md): the HBM fraction is small by construction",
+                         "operative_limits": operative_limits()},
             "cells_flagged_nan_or_bad": bad_flags,
         }
         if world == 1:

@@ -45,7 +45,21 @@ if "--traffic" in sys.argv:
          "kernel": "help_sim_kernel", "report": os.path.basename(rep),
          "dram_bytes_read": val("dram__bytes_read.sum"), "dram_bytes_write": val("dram__bytes_write.sum")}
     d["dram_bytes_per_launch"] = d["dram_bytes_read"] + d["dram_bytes_write"]
-    json.dump(d, open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
+    def num(name):
+        try: return float(r[hdr.index(name)])
+        except (ValueError, IndexError): return None
+    # the counters that bound this kernel (bench.py reports them next to the HBM fraction)
+    d["operative_limits"] = {
+        "source": "%s (ncu --set full)" % os.path.basename(rep),
+        "fp64_pipe_pct_of_peak": num("sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"),
+        "issue_slots_active_pct": num("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+        "lanes_active_of_32": num("smsp__thread_inst_executed_per_inst_executed.ratio"),
+        "warps_active_per_sm": num("sm__warps_active.avg.per_cycle_active"),
+        "l2_hit_pct": num("lts__t_sector_hit_rate.pct"), "l1_hit_pct": num("l1tex__t_sector_hit_rate.pct"),
+        "top_stalls_per_issue": {k: num("smsp__average_warps_issue_stalled_%s_per_issue_active.ratio" % k)
+                                 for k in ("long_scoreboard", "wait", "no_instruction", "not_selected", "barrier")}}
+    old = os.path.join(ROOT, "profiles", "traffic.json")
+    json.dump(d, open(old, "w"), indent=1)
     print(d)
 # hot source lines
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source", "cuda,sass", "--csv"], capture_output=True).stdout.decode("utf-8", "replace")
