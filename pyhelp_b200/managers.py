@@ -31,41 +31,42 @@ KEYS = ("precip", "runoff", "evapo", "perco", "subrun1", "subrun2", "rechg")
 
 
 def load_grid_from_csv(path_togrid: str):
-    """The grid table as a pandas DataFrame indexed by ``cid`` (``pyhelp/managers.py:597-613``)."""
+    """The grid table as a pandas DataFrame indexed by ``cid`` (kept as a column too), cell ids read as
+    strings; the five columns the reference insists on (``pyhelp/managers.py:597-613``) must be there."""
     import pandas as pd
     grid = pd.read_csv(path_togrid, dtype={"cid": "str"})
-    for key in ("cid", "lat_dd", "lon_dd", "run", "context"):
-        if key not in grid.keys():
-            raise KeyError("No attribute '{}' found in {}".format(key, path_togrid))
-    grid.set_index(["cid"], drop=False, inplace=True)
-    return grid
+    missing = [k for k in ("cid", "lat_dd", "lon_dd", "run", "context") if k not in grid.columns]
+    if missing:
+        raise KeyError("No attribute '{}' found in {}".format(missing[0], path_togrid))
+    return grid.set_index("cid", drop=False)
 
 
 def load_weather_from_csv(filename: str):
-    """Daily weather table of a PyHELP weather input file (``pyhelp/managers.py:616-656``): a
-    DataFrame indexed by date (day first) whose columns are the ``(lat_dd, lon_dd)`` of the nodes."""
+    """Daily weather table of a PyHELP weather input file (same result as the reference's loader,
+    ``pyhelp/managers.py:616-656``): a DataFrame indexed by date whose columns are the
+    ``(lat_dd, lon_dd)`` of the nodes.  File layout: free-text header lines, a ``Latitude (dd),...``
+    and a ``Longitude (dd),...`` line, then one ``dd/mm/yyyy,v1,v2,...`` line per day."""
     import pandas as pd
-    with open(filename, "r") as f:
-        rows = list(csv.reader(f, delimiter=","))
-    lat = lon = None
-    first = 0
-    for first, line in enumerate(rows):
-        if not line or not line[0]:
-            continue
-        head = line[0].lower().strip()
-        if head.startswith("lat"):
-            lat = np.array(line[1:]).astype(float)
-        elif head.startswith("lon"):
-            lon = np.array(line[1:]).astype(float)
-        elif lat is not None and lon is not None:
-            break
-    if lat is None or lon is None:
+    coords = {}
+    days, values = [], []
+    with open(filename, "r", newline="") as f:
+        for fields in csv.reader(f):
+            if not fields or not fields[0].strip():
+                continue
+            tag = fields[0].strip().lower()
+            if tag[:3] in ("lat", "lon") and len(coords) < 2:
+                coords[tag[:3]] = np.array([float(x) for x in fields[1:] if x.strip()])
+            elif len(coords) == 2 and tag[:1].isdigit():
+                days.append(fields[0].strip())
+                values.append([float(x) if x.strip() else np.nan for x in fields[1:]])
+    if len(coords) < 2:
         raise ValueError(f"{filename}: no latitude/longitude header lines")
-    data = pd.read_csv(filename, header=None, index_col=[0], skiprows=first, skip_blank_lines=False,
-                       parse_dates=True, dayfirst=True)
-    data.index.name = "date"
-    data.columns = pd.MultiIndex.from_tuples(list(zip(lat, lon)), names=["lat_dd", "lon_dd"])
-    return data
+    nn = coords["lat"].size
+    if coords["lon"].size != nn or any(len(v) != nn for v in values):
+        raise ValueError(f"{filename}: rows do not all have one value per node ({nn})")
+    index = pd.DatetimeIndex(pd.to_datetime(days, dayfirst=True), name="date")
+    columns = pd.MultiIndex.from_arrays([coords["lat"], coords["lon"]], names=["lat_dd", "lon_dd"])
+    return pd.DataFrame(np.asarray(values, dtype=np.float64).reshape(len(days), nn), index=index, columns=columns)
 
 
 class HelpOutput:
