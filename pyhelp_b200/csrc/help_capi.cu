@@ -480,6 +480,7 @@ extern "C" void help_b200_engine_destroy(help_b200_engine* e) { engine_free(e); 
 // ---- diagnostic: evaluate the engine's transcendental functions on the device -----------------
 __global__ void math_eval_kernel(int fn, const double* __restrict__ x, const double* __restrict__ y,
                                  double* __restrict__ out, int64_t n) {
+  helpmath::hm_load_tables();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const double a = x[i], b = y ? y[i] : 0.0;

@@ -453,6 +453,7 @@ __device__ inline float heat_units(int M, int K, float A1, float A2, float A3) {
 __global__ void __launch_bounds__(64)
 help_setup_kernel(BatchDev B, Image img, const int32_t* __restrict__ perm, uint32_t* __restrict__ flags,
                   int32_t* __restrict__ topo, uint64_t* __restrict__ sortkey) {
+  helpmath::hm_load_tables();
   const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // position in the (sorted) image
   if (slot >= B.n_cells) return;
   const int64_t c = perm ? perm[slot] : slot;                            // caller's cell index

@@ -591,6 +591,7 @@ struct Surf {      // REAL*4 surface-process state of one cell
 #endif
 template <int MAXSEG, int THREADS, int REGS>
 __global__ void __launch_bounds__(THREADS) __maxnreg__(REGS) help_sim_kernel(SimArgs A) {
+  helpmath::hm_load_tables();
   const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= A.n_cells) return;
   const Image& img = A.img;
