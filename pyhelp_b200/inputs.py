@@ -41,10 +41,13 @@ def _to_real(txt: np.ndarray, d: int, dtype) -> np.ndarray:
     nz = txt != b""
     if nz.any():
         t = txt[nz]
-        t = np.char.replace(np.char.replace(np.char.replace(t, b" ", b""), b"D", b"E"), b"d", b"e")
-        vals = t.astype(np.float64)
+        try:
+            vals = t.astype(np.float64)                 # plain decimal fields: the usual case
+        except ValueError:                              # embedded blanks (ignored, BN) or a D exponent
+            t = np.char.replace(np.char.replace(np.char.replace(t, b" ", b""), b"D", b"E"), b"d", b"e")
+            vals = t.astype(np.float64)
         if d > 0:
-            nodot = (np.char.find(t, b".") < 0) & (np.char.find(np.char.upper(t), b"E") < 0)
+            nodot = (np.char.find(t, b".") < 0) & (np.char.find(t, b"E") < 0) & (np.char.find(t, b"e") < 0)
             if nodot.any():
                 vals[nodot] = vals[nodot] / (10.0 ** d)
         out[nz] = vals
@@ -55,12 +58,20 @@ def _to_int(txt: np.ndarray) -> np.ndarray:
     out = np.zeros(txt.shape, dtype=np.int32)
     nz = txt != b""
     if nz.any():
-        out[nz] = np.char.replace(txt[nz], b" ", b"").astype(np.int64).astype(np.int32)
+        t = txt[nz]
+        try:
+            out[nz] = t.astype(np.int64).astype(np.int32)
+        except ValueError:
+            out[nz] = np.char.replace(t, b" ", b"").astype(np.int64).astype(np.int32)
     return out
 
 
 def _records(lines, reclen=80) -> np.ndarray:
     a = np.asarray(lines)
+    if a.dtype.kind == "S" and a.dtype.itemsize == reclen:      # already fixed-length records (the cellparams case)
+        rec = np.frombuffer(np.ascontiguousarray(a).tobytes(), dtype=np.uint8).reshape(-1, reclen).copy()
+        rec[rec == 0] = 32                                        # numpy pads short byte strings with NULs
+        return rec
     if a.dtype.kind == "U":
         a = np.char.encode(a, "ascii", "replace")
     a = np.char.ljust(a.reshape(-1).astype(f"S{reclen}"), reclen)
@@ -82,28 +93,32 @@ class WeatherFile:
 
 def read_weather_file(path: str, kind: str) -> WeatherFile:
     """READIN header read (F:1215-1218) + READCD year blocks (F:1100-1129)."""
-    with open(path, "r", errors="replace") as f:
-        lines = f.read().split("\n")
-    if lines and lines[-1] == "":
+    with open(path, "rb") as f:
+        lines = f.read().split(b"\n")
+    if lines and lines[-1] == b"":
         lines.pop()
-    lines = [ln.rstrip("\r") for ln in lines]
     if len(lines) < 4:
         raise ValueError(f"{path}: truncated weather header")
-    hdr = _records(lines[:4])
-    units = int(_to_int(_field(hdr[1:2], 0, 2))[0])
-    header12 = np.array([_to_real(_field(hdr[3:4], 6 * i, 6), 2, F32)[0] for i in range(12)], dtype=F32)
     nblocks = (len(lines) - 4) // 37
     if nblocks < 1:
         raise ValueError(f"{path}: no complete year of data")
-    rec = _records(lines[4:4 + 37 * nblocks])
+    # one byte matrix for the whole file (records cut or blank-padded to 80 columns, CR dropped)
+    allrec = _records(np.array(lines[:4 + 37 * nblocks], dtype="S80"))
+    allrec[allrec == 13] = 32
+    allrec[allrec > 127] = 63
+    hdr, rec = allrec[:4], allrec[4:]
+    units = int(_to_int(_field(hdr[1:2], 0, 2))[0])
+    h12 = np.ascontiguousarray(hdr[3, :72]).reshape(12, 6)
+    header12 = _to_real(np.char.strip(h12.view("S6").reshape(-1)), 2, F32)
     if kind == "D4":      # FORMAT(I10,10F5.2)
         ycol, y_w, v0, v_w, d = 0, 10, 10, 5, 2
     else:                 # FORMAT(I5,10F6.1) / (I5,10F6.0)
         ycol, y_w, v0, v_w = 0, 5, 5, 6
         d = 1 if (kind == "D7" or units == 1) else 0
     yrs = _to_int(_field(rec, ycol, y_w)).reshape(nblocks, 37)[:, -1]
-    cols = [_to_real(_field(rec, v0 + v_w * k, v_w), d, F32) for k in range(10)]
-    data = np.stack(cols, axis=1).reshape(nblocks, 370)[:, :366].astype(F32)
+    vals = np.ascontiguousarray(rec[:, v0:v0 + 10 * v_w]).reshape(-1, v_w)            # [record x 10 fields][v_w]
+    vals = _to_real(np.char.strip(vals.view(f"S{v_w}").reshape(-1)), d, F32)
+    data = vals.reshape(nblocks, 370)[:, :366].astype(F32)
     wf = WeatherFile(kind, units, yrs.astype(np.int32), np.ascontiguousarray(data), header12)
     if kind == "D13":
         wf.idfs = idfs_prescan(data, units)
@@ -306,22 +321,39 @@ def batch_from_cellparams(cellparams: dict) -> CellBatch:
     tp, tt, tr, fp, ft, fr = {}, {}, {}, [], [], []
     cell_f32 = np.zeros((N.HB_NCELL_F32, n), dtype=F32)
     cell_i32 = np.zeros((N.HB_NCELL_I32, n), dtype=np.int32)
-    d10_groups: dict = {}
-    d11_rec = np.zeros((n, 3, 80), dtype=np.uint8)
+    # Records are gathered per cell and converted to byte matrices in a few large calls (one per
+    # D10 record count): the per-cell work is list appends only.
+    def as_s80(a):
+        a = np.asarray(a).reshape(-1)
+        if a.dtype.kind == "U":
+            a = np.char.encode(a, "ascii", "replace")
+        return a if (a.dtype.kind == "S" and a.dtype.itemsize == 80) else np.char.ljust(a.astype("S80"), 80).astype("S80")
+
+    d10_lists: dict = {}
+    d11_list = []
+    node_ids = np.zeros((3, n), dtype=np.int32)
+    tfsoil = np.zeros(n, dtype=np.float64)
+    last = [None, None, None, 0, 0, 0]                       # consecutive cells usually share their weather files
     for i, name in enumerate(names):
         p = cellparams[name]
-        cell_i32[N.HB_NODE_P, i] = node(p[0], "D4", tp, fp)
-        cell_i32[N.HB_NODE_T, i] = node(p[1], "D7", tt, ft)
-        cell_i32[N.HB_NODE_R, i] = node(p[2], "D13", tr, fr)
-        r11 = _records(p[3])
+        for k, (kind, table, order) in enumerate((("D4", tp, fp), ("D7", tt, ft), ("D13", tr, fr))):
+            if p[k] is not last[k]:
+                last[k], last[3 + k] = p[k], node(p[k], kind, table, order)
+            node_ids[k, i] = last[3 + k]
+        r11 = as_s80(p[3])
         if r11.shape[0] < 3:
             raise ValueError(f"cell {name}: D11 needs 3 records")
-        d11_rec[i] = r11[:3]
-        r10 = _records(p[4])
-        d10_groups.setdefault(r10.shape[0], ([], []))
-        d10_groups[r10.shape[0]][0].append(i)
-        d10_groups[r10.shape[0]][1].append(r10)
-        cell_f32[N.HB_TFSOIL, i] = F32(p[11])
+        d11_list.append(r11[:3])
+        r10 = as_s80(p[4])
+        g10 = d10_lists.setdefault(r10.shape[0], ([], []))
+        g10[0].append(i)
+        g10[1].append(r10)
+        tfsoil[i] = p[11]
+    cell_i32[N.HB_NODE_P], cell_i32[N.HB_NODE_T], cell_i32[N.HB_NODE_R] = node_ids
+    cell_f32[N.HB_TFSOIL] = tfsoil.astype(F32)
+    d11_rec = _records(np.concatenate(d11_list)).reshape(n, 3, 80) if n else np.zeros((0, 3, 80), dtype=np.uint8)
+    d10_groups = {nrec: (idx, _records(np.concatenate(recs)).reshape(len(idx), nrec, 80))
+                  for nrec, (idx, recs) in d10_lists.items()}
     max_layers = 1
     for nrec in d10_groups:
         max_layers = max(max_layers, min(20, (nrec - 2) // 2 + 1))
@@ -332,7 +364,7 @@ def batch_from_cellparams(cellparams: dict) -> CellBatch:
     for nrec, (idx, recs) in d10_groups.items():
         if nrec < 3:
             raise ValueError("a D10 input needs at least 3 records")
-        parse_d10(np.stack(recs), cell_f32, cell_i32, layer_f32, layer_i32, layer_rc, np.asarray(idx))
+        parse_d10(recs, cell_f32, cell_i32, layer_f32, layer_i32, layer_rc, np.asarray(idx))
     if n == 0:
         raise ValueError("cellparams is empty")
     used = max(1, int(cell_i32[N.HB_NLAY].max()))
