@@ -85,3 +85,24 @@ def test_deep_family_reaches_the_layer_limit():
     # a barrier-soil layer always has its lateral-drainage layer directly above
     jj, cc = np.nonzero(types == 3)
     assert (types[jj - 1, cc] == 2).all()
+
+
+def test_fixed_length_records_fast_path_equals_the_padded_path(tmp_path):
+    """'S80' arrays go to the byte matrix directly (NUL padding read as blanks); shapes (n,) and (n, 1)
+    (managers.py:410-411 vs pyhelp/tests/test_help3o.py:42-48) and str arrays give the same records."""
+    lines = ["  2", "cell 7", "46.12      112 313   3.50     9.0 10.0 67.9 65.5 74.0 75.7"]
+    padded = inputs._records(np.char.ljust(np.array(lines), 80))              # unicode -> encode -> ljust
+    short = inputs._records(np.array(lines).astype("S80"))                     # NUL-padded S80, fast path
+    col = inputs._records(np.char.ljust(np.array([[x] for x in lines]), 80).astype("S80"))
+    assert padded.shape == (3, 80) and np.array_equal(padded, short) and np.array_equal(padded, col)
+    assert (padded[1, 6:] == 32).all()
+    # a weather file with CRLF line ends and a non-ASCII station name parses like the plain one
+    wx = synth.synth_weather(1, 2001, 1, seed=3)
+    f = synth.write_weather_files(str(tmp_path), wx)["D7"][0]
+    a = inputs.read_weather_file(f, "D7")
+    txt = open(f, "rb").read().split(b"\n")
+    txt[2] = "Rivi\u00e8re du Nord".encode("latin-1")
+    g = tmp_path / "crlf.D7"
+    g.write_bytes(b"\r\n".join(txt))
+    b = inputs.read_weather_file(str(g), "D7")
+    assert np.array_equal(a.data, b.data) and np.array_equal(a.years, b.years) and a.units == b.units
