@@ -21,6 +21,7 @@ per-cell dicts.
 from __future__ import annotations
 
 import ctypes as C
+import os
 import time
 
 import numpy as np
@@ -148,6 +149,46 @@ def run_batch(batch: CellBatch, monthly: bool = True, raw: bool = False, topo: b
         return eng.fetch(topo=topo)
 
 
+def run_batch_devices(batch: CellBatch, n_devices: int, monthly: bool = True) -> dict:
+    """The batch on ``n_devices`` GPUs of this process: contiguous shards of equal estimated cost
+    (:mod:`pyhelp_b200.sharding`), one host thread per device (``help_b200_set_device`` is per thread,
+    the C calls release the GIL), results joined in the caller's cell order.  Cells are independent,
+    so nothing is exchanged between devices.  The torchrun/NCCL route of ``bench.py`` is the measured
+    multi-GPU path; this one serves a caller that stays in one process (opt-in: ``HELP_B200_DEVICES``)."""
+    import threading
+    from . import sharding
+    n_devices = max(1, min(int(n_devices), batch.n_cells))
+    if n_devices == 1:
+        return run_batch(batch, monthly=monthly)
+    ranges = sharding.cost_balanced_ranges(sharding.estimate_cost(batch), n_devices)
+    parts: list = [None] * n_devices
+    errors: list = []
+
+    def work(dev: int, lo: int, hi: int):
+        try:
+            N.set_device(dev)
+            sub = sharding.compact_nodes(batch.take(np.arange(lo, hi)))
+            parts[dev] = run_batch(sub, monthly=monthly)
+        except BaseException as e:                     # re-raised in the caller's thread
+            errors.append(e)
+
+    threads = [threading.Thread(target=work, args=(d, lo, hi)) for d, (lo, hi) in enumerate(ranges) if hi > lo]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errors:
+        raise errors[0]
+    done = [p for p in parts if p is not None]
+    out = {"years": done[0]["years"], "flags": np.concatenate([p["flags"] for p in done])}
+    for key in ("monthly", "yearly", "raw"):
+        if key in done[0]:
+            out[key] = np.concatenate([p[key] for p in done], axis=-1)
+    out["timing_ms"] = {k: max(p["timing_ms"][k] for p in done) for k in done[0]["timing_ms"]}
+    out["n_launches"] = sum(p["n_launches"] for p in done)
+    return out
+
+
 def split_by_cell(batch: CellBatch, res: dict) -> dict:
     """[row][year][month][cell] -> the reference's dict of per-cell dicts."""
     years = res["years"]
@@ -168,7 +209,9 @@ def run_help_allcells(cellparams: dict, ncore=None) -> dict:
         return {}
     N.require_device()          # fail before any host work: this path has no CPU fallback
     batch = batch_from_cellparams(cellparams)
-    res = run_batch(batch, monthly=True)
+    want = os.environ.get("HELP_B200_DEVICES", "1")      # "all" or a count: fan out over several GPUs of this process
+    ndev = N.lib().help_b200_device_count() if want.strip().lower() == "all" else int(want)
+    res = run_batch_devices(batch, ndev, monthly=True) if ndev > 1 else run_batch(batch, monthly=True)
     output = split_by_cell(batch, res)
     print("\nTask completed in %0.2f sec" % (time.perf_counter() - tstart))
     return output

@@ -111,3 +111,53 @@ def test_estimated_cost_ranks_liner_profiles_above_natural_soil():
     assert cl.shape == cn.shape == (n,) and cl.min() > cn.max() and (cn >= 8).all() and (cn <= 16).all()
     sh = sharding.shard_batch(bn, 2, 1, by_cost=True)
     assert abs(sh.n_cells - n // 2) <= 6
+
+
+def test_run_batch_devices_joins_shards_in_caller_order(monkeypatch):
+    """Host logic of the single-process multi-GPU fan-out (processing.run_batch_devices), with the
+    engine stubbed: every shard runs on its own device in its own thread, only with the weather nodes it
+    references, and the results come back in the caller's cell order."""
+    import threading
+    from pyhelp_b200 import processing
+    from pyhelp_b200 import _native as N
+    n, nn, ny = 53, 7, 2
+    g = synth.grid_mixed(n, seed=4)
+    wx = synth.synth_weather(nn, 2001, ny, seed=2)
+    node = synth.assign_nodes(n, nn)
+    b = G.batch_from_grid(g, wx["years_of_day"], wx["precip"], wx["airtemp"], wx["solrad"], node, node, node)
+    seen = {}
+    together = threading.Barrier(3, timeout=30)           # the three shards must be in flight at the same time
+
+    def fake_set_device(dev):
+        seen.setdefault(threading.get_ident(), []).append(dev)
+
+    def fake_run_batch(sub, monthly=True, raw=False, topo=False):
+        # a value that identifies the cell: its CN2 and the first precipitation value of ITS node (after compaction)
+        tag = sub.cell_f32[N.HB_CN2] + sub.pre[sub.cell_i32[N.HB_NODE_P], 0, 0]
+        m = np.broadcast_to(tag.astype(np.float32), (N.HR_NROWS, sub.n_years, 12, sub.n_cells)).copy()
+        y = np.broadcast_to(tag.astype(np.float32), (N.HY_NROWS, sub.n_years, sub.n_cells)).copy()
+        assert sub.pre.shape[0] == np.unique(sub.cell_i32[N.HB_NODE_P]).size          # compacted weather
+        if together is not None:
+            together.wait()
+        return {"years": sub.years.astype(np.uint16), "flags": np.zeros(sub.n_cells, np.uint32), "monthly": m, "yearly": y,
+                "timing_ms": {"h2d": 1.0, "setup": 1.0, "simulate": float(sub.n_cells), "d2h": 1.0}, "n_launches": 4}
+
+    monkeypatch.setattr(N, "set_device", fake_set_device)
+    monkeypatch.setattr(processing, "run_batch", fake_run_batch)
+    r = processing.run_batch_devices(b, 3)
+    want = b.cell_f32[N.HB_CN2] + b.pre[b.cell_i32[N.HB_NODE_P], 0, 0]
+    assert r["monthly"].shape == (N.HR_NROWS, ny, 12, n) and r["yearly"].shape == (N.HY_NROWS, ny, n)
+    assert np.array_equal(r["monthly"][0, 0, 0], want.astype(np.float32)) and np.array_equal(r["yearly"][2, 1], want.astype(np.float32))
+    assert r["flags"].shape == (n,) and r["n_launches"] == 12
+    assert sorted(d for v in seen.values() for d in v) == [0, 1, 2] and len(seen) == 3          # one thread per device
+    together = None
+    # one device: the plain path; more devices than cells: clipped
+    assert processing.run_batch_devices(b, 1)["monthly"].shape[-1] == n
+    tiny = b.take(np.arange(2))
+    assert processing.run_batch_devices(tiny, 8)["yearly"].shape[-1] == 2
+    # an error on one device surfaces in the caller
+    def boom(sub, monthly=True, raw=False, topo=False):
+        raise N.EngineError("device lost")
+    monkeypatch.setattr(processing, "run_batch", boom)
+    with pytest.raises(N.EngineError):
+        processing.run_batch_devices(b, 2)
