@@ -190,6 +190,16 @@ int help_b200_nearest_nodes(int64_t n_cells, const double* cell_lat, const doubl
                             int32_t n_nodes, const double* node_lat, const double* node_lon,
                             int32_t* out_index);
 
+/* The reference's weather-file round trip for a whole table (8f row 1):
+ * save_precip/airtemp/solrad_to_HELP print every daily value with '{:>5.1f}' / '{:>6.1f}' / '{:>6.2f}'
+ * (pyhelp/weather_reader.py:31,44,57) and READCD reads the text back as REAL*4
+ * (pyhelp/HELP3O.FOR:1100-1129).  table[n_days][n_nodes] float64 (mm, deg C or MJ/m2, host) ->
+ * out[n_nodes][n_years][HELP_B200_DAYS] float32 = float32(float(format(x, '.{decimals}f'))), zero
+ * beyond a year's days: the layout of help_b200_batch.pre/tmp/rad.  year_day0[y] / year_ndays[y] =
+ * first row and number of rows of year y in the table.  Host pointers.                          */
+int help_b200_pack_weather(const double* table, int64_t n_days, int32_t n_nodes, const int32_t* year_day0,
+                           const int32_t* year_ndays, int32_t n_years, int32_t decimals, float* out);
+
 /* Daily channel: the reference's daily output (IOD = 1: OUTDAY,
  * HELP3O.FOR:5984-6029, parsed by read_daily_help_output, pyhelp/processing.py:150-220) for a
  * few selected cells -- a verification channel, not a bulk output.  select_daily() before

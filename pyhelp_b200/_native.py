@@ -105,6 +105,8 @@ def lib():
     L.help_b200_engine_post_process.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     L.help_b200_nearest_nodes.restype = C.c_int
     L.help_b200_nearest_nodes.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.help_b200_pack_weather.restype = C.c_int
+    L.help_b200_pack_weather.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
     if L.help_b200_abi_version() != 1:
         raise EngineError("libhelp_b200.so ABI version mismatch; rebuild")
     _lib = L

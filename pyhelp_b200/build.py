@@ -11,8 +11,13 @@ HERE = osp.dirname(osp.abspath(__file__))
 SRC = osp.join(HERE, "csrc")
 OUT = osp.join(HERE, "libhelp_b200.so")
 SOURCES = ["help_capi.cu"]
-DEPS = ["help_capi.cu", "help_sim.cuh", "help_setup.cuh", "help_image.h", "help_math.h", "help_math_tables.h",
-        "../../include/help_b200.h"]
+
+
+def deps() -> list:
+    """Every source the library is built from: all of csrc/ plus the public header."""
+    import glob
+    return sorted(glob.glob(osp.join(SRC, "*.cu")) + glob.glob(osp.join(SRC, "*.cuh")) + glob.glob(osp.join(SRC, "*.h"))) + \
+        [osp.join(HERE, "..", "include", "help_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -34,7 +39,7 @@ def needs_build() -> bool:
     if not osp.exists(OUT):
         return True
     t = osp.getmtime(OUT)
-    return any(osp.getmtime(osp.join(SRC, d)) > t for d in DEPS)
+    return any(osp.getmtime(d) > t for d in deps())
 
 
 def build(force: bool = False, verbose: bool = False, out: str | None = None, defines=()) -> str:

@@ -24,6 +24,7 @@
 #include "help_sim.cuh"
 #include "help_nodes.cuh"
 #include "help_post.cuh"
+#include "help_weather.cuh"
 
 using namespace helpb200;
 
@@ -413,8 +414,11 @@ extern "C" int help_b200_engine_select_daily(help_b200_engine* e, const int32_t*
   for (int y = 0; y < e->ny; ++y) e->daily_days += (years[y] % 4 == 0) ? 366 : 365;      // LEAP, F:1048
   int rc;
   if ((rc = dev_alloc(&e->d_daily_row, (size_t)e->n)) || (rc = dev_alloc(&e->d_daily, (size_t)n_selected * e->daily_days * kDailyCols))) return rc;
-  CU(cudaMemcpy(e->d_daily_row, row.data(), sizeof(int32_t) * e->n, cudaMemcpyHostToDevice));
-  CU(cudaMemset(e->d_daily, 0, sizeof(double) * (size_t)n_selected * e->daily_days * kDailyCols));
+  // on the engine's stream and complete on return: the legacy default stream does not order against
+  // e->stream (non-blocking) or a caller's stream, where the next simulate() runs
+  CU(cudaMemcpyAsync(e->d_daily_row, row.data(), sizeof(int32_t) * e->n, cudaMemcpyHostToDevice, e->stream));
+  CU(cudaMemsetAsync(e->d_daily, 0, sizeof(double) * (size_t)n_selected * e->daily_days * kDailyCols, e->stream));
+  CU(cudaStreamSynchronize(e->stream));
   e->n_daily = n_selected;
   return 0;
 }
@@ -560,6 +564,36 @@ extern "C" int help_b200_nearest_nodes(int64_t n_cells, const double* cell_lat, 
   }
   if (ce == cudaSuccess) ce = cudaMemcpy(out_index, d_out, sizeof(int32_t) * n_cells, cudaMemcpyDeviceToHost);
   if (ce != cudaSuccess) return done(fail(HELP_B200_ECUDA, "nearest_nodes", ce));
+  return done(0);
+}
+
+extern "C" int help_b200_pack_weather(const double* table, int64_t n_days, int32_t n_nodes, const int32_t* year_day0,
+                                      const int32_t* year_ndays, int32_t n_years, int32_t decimals, float* out) {
+  if (!table || !year_day0 || !year_ndays || !out || n_days < 1 || n_nodes < 1 || n_years < 1 || decimals < 0 || decimals > 15)
+    return fail(HELP_B200_EINVAL, "pack_weather: bad argument");
+  for (int y = 0; y < n_years; ++y)
+    if (year_day0[y] < 0 || year_ndays[y] < 0 || year_ndays[y] > kDays || (int64_t)year_day0[y] + year_ndays[y] > n_days)
+      return fail(HELP_B200_EINVAL, "pack_weather: a year's day range is outside the table");
+  if (help_b200_device_count() < 1) return fail(HELP_B200_ENODEV, "no CUDA device (this engine has no CPU path)");
+  double* d_tab = nullptr; float* d_out = nullptr; int32_t *d_d0 = nullptr, *d_nd = nullptr;
+  int rc = 0;
+  auto done = [&](int code) { cudaDeviceSynchronize(); dev_free(d_tab); dev_free(d_out); dev_free(d_d0); dev_free(d_nd); return code; };
+  const size_t n_in = (size_t)n_days * n_nodes, n_out = (size_t)n_nodes * n_years * kDays;
+  if ((rc = dev_alloc(&d_tab, n_in)) || (rc = dev_alloc(&d_out, n_out)) || (rc = dev_alloc(&d_d0, (size_t)n_years)) ||
+      (rc = dev_alloc(&d_nd, (size_t)n_years)))
+    return done(rc);
+  cudaError_t ce = cudaMemcpy(d_tab, table, sizeof(double) * n_in, cudaMemcpyHostToDevice);
+  if (ce == cudaSuccess) ce = cudaMemcpy(d_d0, year_day0, sizeof(int32_t) * n_years, cudaMemcpyHostToDevice);
+  if (ce == cudaSuccess) ce = cudaMemcpy(d_nd, year_ndays, sizeof(int32_t) * n_years, cudaMemcpyHostToDevice);
+  if (ce == cudaSuccess) {
+    double S = 1.0;
+    for (int k = 0; k < decimals; ++k) S *= 10.0;
+    const dim3 grid((kDays + 31) / 32, (unsigned)n_years, (unsigned)((n_nodes + 31) / 32));
+    pack_weather_kernel<<<grid, dim3(32, 8)>>>(d_tab, (int64_t)n_nodes, d_d0, d_nd, n_years, S, d_out);
+    ce = cudaGetLastError();
+  }
+  if (ce == cudaSuccess) ce = cudaMemcpy(out, d_out, sizeof(float) * n_out, cudaMemcpyDeviceToHost);
+  if (ce != cudaSuccess) return done(fail(HELP_B200_ECUDA, "pack_weather", ce));
   return done(0);
 }
 

@@ -592,15 +592,22 @@ struct Surf {      // REAL*4 surface-process state of one cell
 template <int MAXSEG, int THREADS, int REGS>
 __global__ void __launch_bounds__(THREADS) __maxnreg__(REGS) help_sim_kernel(SimArgs A) {
   helpmath::hm_load_tables();
-  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= A.n_cells) return;
+  // No thread leaves before the end: the day barrier below must be reached by every thread of the
+  // block the same number of times.  A thread past the end of the batch, or one whose cell cannot
+  // be simulated, reads the last cell's constants (valid addresses) and sits out every day
+  // (`live == false`); it only keeps the barrier count.
+  const int64_t s_raw = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  bool live = s_raw < A.n_cells;
+  const int64_t s = live ? s_raw : A.n_cells - 1;
   const Image& img = A.img;
   const int64_t n = A.n_cells;
   const int64_t cell = A.perm ? A.perm[s] : s;
   const int NY = A.n_years;
   uint32_t flag = (uint32_t)img.I(I_FLAGS, s);
-  const int NSEG = img.I(I_NSEG, s);
-  if (NSEG <= 0 || NSEG > MAXSEG) {
+  const int NSEG_img = img.I(I_NSEG, s);
+  const bool badcell = (NSEG_img <= 0 || NSEG_img > MAXSEG);
+  const int NSEG = badcell ? 0 : NSEG_img;
+  if (badcell && live) {
     flag |= kFlagBadCell;
     const float qnan = __int_as_float(0x7fc00000);
     for (int y = 0; y < NY; ++y) {
@@ -611,8 +618,8 @@ __global__ void __launch_bounds__(THREADS) __maxnreg__(REGS) help_sim_kernel(Sim
       if (A.yearly) for (int r = 0; r < 5; ++r) A.yearly[((int64_t)r * NY + y) * n + cell] = qnan;
     }
     A.flags[cell] = flag;
-    return;
   }
+  if (badcell) live = false;
   // ---- constants of this cell --------------------------------------------------------------
   const float EDEPTH = img.F(F_EDEPTH, s), SEDEP = img.F(F_SEDEP, s), SMXN = img.F(F_SMXN, s),
               SMXF = img.F(F_SMXF, s), FRUNOF = img.F(F_FRUNOF, s), CONA = img.F(F_CONA, s),
@@ -695,9 +702,16 @@ __global__ void __launch_bounds__(THREADS) __maxnreg__(REGS) help_sim_kernel(Sim
   const float UADJ = 0.262f * (1.0f + 0.24f * WIND);
   const float SFNEW = 1.5f * 24.f, RFMIN = 0.25f * 24.f;
 
-  for (;;) {                                            // label 1060: spin-up pass, then the reported pass
+  // label 1060: the spin-up pass (IPRE < 2: one year, F:986-996), then the reported pass.  The pass
+  // and year loops are block-uniform -- a block runs the spin-up year iff one of its cells needs it --
+  // and a thread that is not part of a pass (`act == false`) only keeps the day barrier.
+  const bool my_spin = live && IPRE < 2;
+  const bool blk_spin = __syncthreads_or(my_spin ? 1 : 0) != 0;
+  for (int pass = blk_spin ? 0 : 1; pass < 2; ++pass) {
+    const bool act = live && (pass == 1 || my_spin);
     // SNOCOEF (F:3636-3751)
-    if (IPRE < 2) {
+    if (!act) {
+    } else if (IPRE < 2) {
       U.TWE = U.WE = U.XNEGHS = U.XLIQW = U.TINDEX = U.STORGE = 0.f;
       for (int k = 1; k <= 4; ++k) U.EXLAG[k] = 0.f;
       if (U.OSNO > 0.f && IPRE == 1) { U.XLIQW = (U.OSNO * 25.4f) * PLQW; U.WE = (U.OSNO * 25.4f) - U.XLIQW; U.SNO = U.OSNO; }
@@ -719,14 +733,14 @@ __global__ void __launch_bounds__(THREADS) __maxnreg__(REGS) help_sim_kernel(Sim
       U.OSNO = U.OLDSNO; U.SNO = U.OLDSNO;
     }
     // SETUPS second pass (F:2673-2741)
-    if (IPRE >= 2) {
+    if (act && IPRE >= 2) {
       U.ADDRUN = 0.0f;
       for (int k = 2; k <= 6; ++k) EXWAT[k] = 0.0f;
       if (IPRE == 3) for (int J = 1; J <= NSEG; ++J) SWa(J) = (double)img.SF(S_SW0, J, s);
       for (int J = 1; J <= NSEG; ++J) BALa(J) = 0.0;
     }
-    const bool report = (IPRE >= 2);
-    const int dsel = (A.daily && report) ? A.daily_row[cell] : -1;
+    const bool report = (pass == 1);                    // == (IPRE >= 2) for the threads of this pass
+    const int dsel = (A.daily && report && act) ? A.daily_row[cell] : -1;
     int64_t drow = 0;
     bool it_snow = false;
     const int npass_years = report ? NY : 1;
@@ -742,11 +756,9 @@ __global__ void __launch_bounds__(THREADS) __maxnreg__(REGS) help_sim_kernel(Sim
       const float* __restrict__ yrad = wrad + (int64_t)iy * kDays;
       for (int IDA = 1; IDA <= ND; ++IDA) {               // DO 1100
 #ifdef HELP_SIM_DAYSYNC
-#ifndef HELP_SIM_SYNC_MASK
-#define HELP_SIM_SYNC_MASK 0
+        __syncthreads();      // keep the block's warps in the same code region (instruction cache); reached by every thread of the block
 #endif
-        if ((IDA & HELP_SIM_SYNC_MASK) == 0) __syncthreads();      // keep the block's warps in the same code region (instruction cache)
-#endif
+        if (!act) continue;
         const float PRE = __ldg(ypre + IDA - 1), TMPF = __ldg(ytmp + IDA - 1), RAD = __ldg(yrad + IDA - 1);
         const float RH = RHq[(IDA <= 91) ? 0 : (IDA <= 182) ? 1 : (IDA <= 274) ? 2 : 3];
         PREM = PREM + PRE;
@@ -1394,21 +1406,19 @@ __global__ void __launch_bounds__(THREADS) __maxnreg__(REGS) help_sim_kernel(Sim
           if (MO < 12) { MO = MO + 1; mend = kICAL[MO]; }
         }
       }   // day
+      if (!act) continue;
       if (report && A.yearly) {
         for (int r = 0; r < 5; ++r) A.yearly[((int64_t)r * NY + iy) * n + cell] = ysum[r];
       }
       // year end (F:938-996)
       U.OLDSNO = U.ADDRUN + U.SNO;
-      if (IPRE < 2) {
+      if (IPRE < 2) {               // the spin-up pass is this one year
         IPRE = IPRE + 2;
         for (int J = 1; J <= NSEG; ++J) { SWa(J) = SWa(J) + BALa(J) / 2.0; BALa(J) = 0.0; }
-        break;
       }
     }   // year
-    if (!report) continue;
-    break;
   }
-  A.flags[cell] = flag;
+  if (live) A.flags[cell] = flag;
 }
 
 }  // namespace helpb200

@@ -21,7 +21,7 @@ from __future__ import annotations
 import numpy as np
 
 from . import _native as N
-from .inputs import CellBatch, F32, idfs_prescan
+from .inputs import CellBatch, F32
 
 MINEDEPTH, MAXEDEPTH, MINTHICK = 3, 80, 10        # preprocessing.py:20-22
 
@@ -44,51 +44,64 @@ def quantize(x, d: int) -> np.ndarray:
     return out + 0.0          # -0.0 -> 0.0 is irrelevant to the Fortran read
 
 
-def calc_dist_from_coord(lat1, lon1, lat2, lon2):
-    """Haversine distance in km (reference pyhelp/utils.py:81-96)."""
-    lat1, lon1 = np.radians(lat1), np.radians(lon1)
-    lat2, lon2 = np.radians(lat2), np.radians(lon2)
-    r = 6373
-    dlon = lon2 - lon1
-    dlat = lat2 - lat1
-    a = np.sin(dlat / 2) ** 2 + np.cos(lat1) * np.cos(lat2) * np.sin(dlon / 2) ** 2
-    c = 2 * np.arctan2(np.sqrt(a), np.sqrt(1 - a))
-    return r * c
-
-
-def nearest_nodes(cell_lat, cell_lon, node_lat, node_lon, chunk: int = 8192) -> np.ndarray:
-    """argmin of the haversine distance per cell (first minimum wins, like np.argmin
-    in managers.py:313), evaluated in cell chunks to bound memory."""
-    cell_lat, cell_lon = np.asarray(cell_lat, float), np.asarray(cell_lon, float)
-    node_lat, node_lon = np.asarray(node_lat, float), np.asarray(node_lon, float)
-    out = np.empty(cell_lat.shape[0], dtype=np.int32)
-    for a in range(0, cell_lat.shape[0], chunk):
-        b = min(a + chunk, cell_lat.shape[0])
-        d = calc_dist_from_coord(cell_lat[a:b, None], cell_lon[a:b, None], node_lat[None, :], node_lon[None, :])
-        out[a:b] = np.argmin(d, axis=1)
-    return out
-
-
-def weather_to_nodes(years_of_day: np.ndarray, values: np.ndarray, decimals: int):
-    """[day][node] table -> [node][year][368] float32 as the engine reads a D4/D7/D13
-    file written by weather_reader.py (values quantised to `decimals`)."""
+def _year_blocks(years_of_day: np.ndarray):
+    """(years, first row, number of rows) of every calendar year of a daily table; the row counts must
+    be the ones weather_reader.py:87 pads to (calendar.isleap)."""
     years_of_day = np.asarray(years_of_day)
-    years = np.unique(years_of_day)
+    years, day0, ndays = np.unique(years_of_day, return_index=True, return_counts=True)
+    if not (np.diff(years_of_day) >= 0).all():
+        raise ValueError("the daily table must be in chronological order")
+    for y, k in zip(years.tolist(), ndays.tolist()):
+        nd = 366 if (y % 4 == 0 and (y % 100 != 0 or y % 400 == 0)) else 365
+        if k != nd:
+            raise ValueError(f"year {y} has {k} days of data, expected {nd}")
+    return years.astype(np.int32), day0.astype(np.int32), ndays.astype(np.int32)
+
+
+def weather_to_nodes(years_of_day: np.ndarray, values: np.ndarray, decimals: int, where: str = "host"):
+    """[day][node] table -> [node][year][368] float32 as the engine reads a D4/D7/D13
+    file written by weather_reader.py (values quantised to `decimals`).  ``where="device"`` runs the
+    format/read round trip and the transposition on the GPU (``help_b200_pack_weather``,
+    ``csrc/help_weather.cuh``; same bits, tests/test_gpu_pack.py) -- the host version costs 0.4 s
+    per variable per 1000 nodes x 30 yr and is what a caller without a device at packing time uses."""
+    years, day0, ndays = _year_blocks(years_of_day)
+    values = np.asarray(values, dtype=np.float64)
     nn = values.shape[1]
     out = np.zeros((nn, years.size, N.DAYS), dtype=F32)
+    if where == "device":
+        tab = np.ascontiguousarray(values)
+        N.require_device()
+        N.check(N.lib().help_b200_pack_weather(N.ptr(tab), tab.shape[0], nn, N.ptr(day0), N.ptr(ndays), years.size,
+                                               int(decimals), N.ptr(out)), "pack_weather")
+        return years, out
+    if where != "host":
+        raise ValueError("where must be 'host' or 'device'")
     q = quantize(values, decimals).astype(F32)
-    for k, y in enumerate(years):
-        sel = np.nonzero(years_of_day == y)[0]
-        nd = 366 if (y % 4 == 0 and (y % 100 != 0 or y % 400 == 0)) else 365      # calendar.isleap (weather_reader.py:87)
-        if sel.size != nd:
-            raise ValueError(f"year {y} has {sel.size} days of data, expected {nd}")
-        out[:, k, :nd] = q[sel].T
-    return years.astype(np.int32), out
+    for k in range(years.size):
+        out[:, k, :ndays[k]] = q[day0[k]:day0[k] + ndays[k]].T
+    return years, out
+
+
+def idfs_prescan_nodes(rad: np.ndarray, iu13: int = 2) -> np.ndarray:
+    """:func:`pyhelp_b200.inputs.idfs_prescan` for every node at once: int32 [n_nodes][2] from the
+    [node][year][368] radiation (float32 sequential accumulation over years x 31 days, F:1352-1373)."""
+    rad = np.asarray(rad, dtype=F32)[:, :100]
+    nn, nyrs = rad.shape[0], rad.shape[1]
+    out = np.empty((nn, 2), dtype=np.int32)
+    for h, (lo, hi) in enumerate(((334, 365), (151, 182))):
+        seq = np.ascontiguousarray(rad[:, :, lo:hi]).reshape(nn, -1)
+        radtot = np.cumsum(seq, axis=1, dtype=F32)[:, -1]
+        radavg = (radtot / F32(nyrs)) / F32(31) if nyrs > 1 else radtot / F32(31)
+        if iu13 != 1:
+            radavg = radavg * F32(23.89)
+        radavg = radavg.astype(F32)
+        out[:, h] = np.maximum((F32(35.4) - (F32(0.154) * radavg).astype(F32)).astype(F32).astype(np.int32), 1)
+    return out
 
 
 def batch_from_grid(grid: dict, years_of_day, precip, airtemp, solrad, node_p, node_t, node_r,
                     solrad_lat=None, tfsoil_c: float = 0.0, sf_edepth: float = 1.0, sf_ulai: float = 1.0,
-                    sf_cn: float = 1.0, extra_layers: dict | None = None) -> CellBatch:
+                    sf_cn: float = 1.0, extra_layers: dict | None = None, weather: str = "host") -> CellBatch:
     """Vectorised `format_d10d11_inputs` + weather formatting + Fortran read.
 
     ``grid``: mapping column -> array over cells with the columns of docs/data.rst
@@ -97,6 +110,8 @@ def batch_from_grid(grid: dict, years_of_day, precip, airtemp, solrad, node_p, n
     ``precip``/``airtemp``/``solrad``: [day][node] tables in mm, deg C, MJ/m2/day.
     ``extra_layers``: optional per-layer design fields PyHELP's formatter leaves blank
     (phole{i}, defec{i}, ipq{i}, trans{i}, recir{i}, layr{i}, subin{i}) for landfill designs.
+    ``weather``: ``"host"`` or ``"device"`` -- where the weather tables are quantised and laid out
+    (:func:`weather_to_nodes`).
     Cells PyHELP would skip (nlayer == 0 or a -9999 layer field,
     preprocessing.py:32-35,150-153) must be removed by the caller (`runnable_cells`).
     """
@@ -158,11 +173,11 @@ def batch_from_grid(grid: dict, years_of_day, precip, airtemp, solrad, node_p, n
             layer_i32[N.HL_LAYR, j] = col("layr").astype(np.int32)
             if f"thick_exact{s}" in ex:          # landfill liners are thinner than MINTHICK
                 layer_f32[N.HL_THICK, j] = np.where(on, np.asarray(ex[f"thick_exact{s}"], dtype=float), 0)
-    years, pre = weather_to_nodes(years_of_day, np.asarray(precip, float), 1)
-    _, tmp = weather_to_nodes(years_of_day, np.asarray(airtemp, float), 1)
-    _, rad = weather_to_nodes(years_of_day, np.asarray(solrad, float), 2)
+    years, pre = weather_to_nodes(years_of_day, precip, 1, weather)
+    _, tmp = weather_to_nodes(years_of_day, airtemp, 1, weather)
+    _, rad = weather_to_nodes(years_of_day, solrad, 2, weather)
     npn, ntn, nrn = pre.shape[0], tmp.shape[0], rad.shape[0]
-    idfs = np.array([idfs_prescan(rad[i, :, :366], 2) for i in range(nrn)], dtype=np.int32).reshape(-1, 2)
+    idfs = idfs_prescan_nodes(rad, 2)
     names = [str(c) for c in g["cid"].tolist()] if "cid" in g else [str(i) for i in range(n)]
     return CellBatch(
         n, int(years.size), L, np.ascontiguousarray(years), pre, tmp, rad,

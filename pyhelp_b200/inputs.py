@@ -47,7 +47,7 @@ def _to_real(txt: np.ndarray, d: int, dtype) -> np.ndarray:
             t = np.char.replace(np.char.replace(np.char.replace(t, b" ", b""), b"D", b"E"), b"d", b"e")
             vals = t.astype(np.float64)
         if d > 0:
-            nodot = (np.char.find(t, b".") < 0) & (np.char.find(t, b"E") < 0) & (np.char.find(t, b"e") < 0)
+            nodot = np.char.find(t, b".") < 0          # Fw.d: no point -> the last d digits of the significand are decimals, exponent or not
             if nodot.any():
                 vals[nodot] = vals[nodot] / (10.0 ** d)
         out[nz] = vals
@@ -121,7 +121,11 @@ def read_weather_file(path: str, kind: str) -> WeatherFile:
     data = vals.reshape(nblocks, 370)[:, :366].astype(F32)
     wf = WeatherFile(kind, units, yrs.astype(np.int32), np.ascontiguousarray(data), header12)
     if kind == "D13":
-        wf.idfs = idfs_prescan(data, units)
+        # READIN's pre-scan reads the same fields with F6.1 whatever the units (formats 5400/5410,
+        # F:1364-1365) while READCD reads SI files with F6.0 (F:1128): fields written without a
+        # decimal point are ten times smaller in the pre-scan
+        pre = data if d == 1 else _to_real(np.char.strip(np.ascontiguousarray(rec[:, v0:v0 + 10 * v_w]).reshape(-1, v_w).view(f"S{v_w}").reshape(-1)), 1, F32).reshape(nblocks, 370)[:, :366]
+        wf.idfs = idfs_prescan(pre, units)
     return wf
 
 

@@ -86,9 +86,16 @@ class HelpOutput:
         """``HelpOutput.calc_area_yearly_avg`` (``pyhelp/output.py:154-169``): {var: [Ny]} mm/yr."""
         return {k: np.sum(v, axis=1) for k, v in self._area.items()}
 
-    def calc_cells_yearly_avg(self) -> dict:
-        """``HelpOutput.calc_cells_yearly_avg`` (``pyhelp/output.py:171-203``, all years): {var: [Np]}."""
-        return self._cells
+    def calc_cells_yearly_avg(self, year_from=-np.inf, year_to=np.inf) -> dict:
+        """``HelpOutput.calc_cells_yearly_avg`` (``pyhelp/output.py:171-203``): {var: [Np]} mm/yr, averaged
+        over the years of ``[year_from, year_to]``.  The default window is the device-side reduction
+        computed while the engine was alive; a narrower one is evaluated from ``data`` like the
+        reference does."""
+        years = np.asarray(self.data["years"])
+        mask = (years >= year_from) & (years <= year_to)
+        if mask.all():
+            return self._cells
+        return {k: np.mean(np.sum(self.data[k][:, mask, :], axis=2), axis=1) for k in KEYS}
 
 
 def _canonical_nodes(node: np.ndarray, lat: np.ndarray, lon: np.ndarray, fext: str) -> np.ndarray:
@@ -136,7 +143,12 @@ class HelpManager:
         """Monthly water budget of every runnable cell of ``cellnames`` (``pyhelp/managers.py:342-446``).
         ``tfsoil`` in deg C.  Cells with a -9999 layer field are skipped with the reference's warning."""
         if path_to_hdf5 or build_help_input_files:
+            # kept in the signature so that reference call sites bind; the reference's own HelpManager serves
+            # these two options (patch_pyhelp() routes only run_help_allcells here)
             raise NotImplementedError("HDF5 output and D10/D11 debug files are outside the hot path (DESIGN.md section 8)")
+        for name, v in (("sf_edepth", sf_edepth), ("sf_ulai", sf_ulai), ("sf_cn", sf_cn)):
+            if v < 0:                                             # pyhelp/managers.py:246-251
+                raise ValueError(f"{name} value cannot be lower than 0.")
         if self.grid is None or self.precip_data is None or self.airtemp_data is None or self.solrad_data is None:
             raise ValueError("grid, precip, airtemp and solrad tables are required")
         run = self.get_run_cellnames(cellnames)
@@ -173,29 +185,5 @@ class HelpManager:
             eng.simulate()
             res = eng.fetch(monthly=True, yearly=False)
             red = eng.post_process(context=context)
-        data = post_process_monthly(res["monthly"], res["years"], names, context, cols["lat_dd"], cols["lon_dd"])
+        data = processing.post_process_monthly(res["monthly"], res["years"], names, context, cols["lat_dd"], cols["lon_dd"])
         return HelpOutput(data, red["area_monthly_avg"], red["cells_yearly_avg"])
-
-
-def post_process_monthly(monthly: np.ndarray, years, cellnames, context, lat_dd, lon_dd) -> dict:
-    """``_post_process_output`` (``pyhelp/managers.py:448-506``) on the engine's
-    ``[row][year][month][cell]`` float32 buffer, vectorised: (Np, Ny, 12) float64 arrays, NaN cells
-    listed, recharge of ``context == 2`` cells added to ``subrun1`` (or ``subrun2`` when the cell has
-    any) and zeroed."""
-    rows = ("precip", "runoff", "evapo", "subrun1", "subrun2", "perco", "rechg")          # engine row order
-    data = {k: np.ascontiguousarray(np.transpose(monthly[i], (2, 0, 1))).astype(np.float64) for i, k in enumerate(rows)}
-    data = {k: data[k] for k in KEYS}
-    rechg = data["rechg"]
-    nan = np.isnan(rechg).any(axis=(1, 2))
-    stream = (np.asarray(context) == 2) & ~nan
-    deep = stream & ~(data["subrun2"] == 0).all(axis=(1, 2))
-    shallow = stream & ~deep
-    data["subrun1"][shallow] += rechg[shallow]
-    data["subrun2"][deep] += rechg[deep]
-    rechg[stream] = 0.0
-    data["cid"] = list(cellnames)
-    data["years"] = np.asarray(years)
-    data["idx_nan"] = np.nonzero(nan)[0].tolist()
-    data["lat_dd"] = np.asarray(lat_dd)
-    data["lon_dd"] = np.asarray(lon_dd)
-    return data

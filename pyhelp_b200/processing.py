@@ -224,35 +224,38 @@ def run_help_singlecell(item):
     return (cellname, out[cellname])
 
 
-def post_process_output(output: dict, context=None, lat_dd=None, lon_dd=None) -> dict:
-    """``HelpManager._post_process_output`` (reference pyhelp/managers.py:448-506):
-    per-cell dicts -> the ``HelpOutput.data`` layout, (Np, Ny, 12) float64 arrays,
-    recharge of ``context == 2`` cells redistributed to subsurface runoff."""
-    cellnames = list(output.keys())
-    years = output[cellnames[0]]["years"]
-    Np, Ny = len(cellnames), len(years)
-    keys = ["precip", "runoff", "evapo", "perco", "subrun1", "subrun2", "rechg"]
-    data = {key: np.zeros((Np, Ny, 12)) for key in keys}
-    data["cid"] = cellnames
-    data["years"] = years
-    data["idx_nan"] = []
+POST_KEYS = ("precip", "runoff", "evapo", "perco", "subrun1", "subrun2", "rechg")
+
+
+def post_process_monthly(monthly: np.ndarray, years, cellnames, context, lat_dd=None, lon_dd=None) -> dict:
+    """``HelpManager._post_process_output`` (reference ``pyhelp/managers.py:448-506``) on the engine's
+    ``[row][year][month][cell]`` float32 buffer, vectorised: the ``HelpOutput.data`` layout, (Np, Ny, 12)
+    float64 arrays, NaN cells listed in ``idx_nan``, recharge of ``context == 2`` cells added to
+    ``subrun1`` (or ``subrun2`` when the cell has any) and zeroed."""
+    data = {k: np.ascontiguousarray(np.transpose(monthly[i], (2, 0, 1))).astype(np.float64) for i, k in enumerate(KEYS)}
+    data = {k: data[k] for k in POST_KEYS}
+    rechg = data["rechg"]
+    nan = np.isnan(rechg).any(axis=(1, 2))
+    ctx = np.zeros(rechg.shape[0], dtype=np.int64) if context is None else np.asarray(context)
+    stream = (ctx == 2) & ~nan
+    deep = stream & ~(data["subrun2"] == 0).all(axis=(1, 2))
+    shallow = stream & ~deep
+    data["subrun1"][shallow] += rechg[shallow]
+    data["subrun2"][deep] += rechg[deep]
+    rechg[stream] = 0.0
+    data["cid"] = list(cellnames)
+    data["years"] = np.asarray(years)
+    data["idx_nan"] = np.nonzero(nan)[0].tolist()
     if lat_dd is not None:
         data["lat_dd"] = np.asarray(lat_dd)
     if lon_dd is not None:
         data["lon_dd"] = np.asarray(lon_dd)
-    ctx = [0] * Np if context is None else list(context)
-    for i, cellname in enumerate(cellnames):
-        o = output[cellname]
-        for key in keys[:-1]:
-            data[key][i, :, :] = o[key]
-        if np.any(np.isnan(o["rechg"])):
-            data["idx_nan"].append(i)
-            data["rechg"][i, :, :] = o["rechg"]
-        elif ctx[i] == 2:
-            if np.all(o["subrun2"] == 0):
-                data["subrun1"][i, :, :] += o["rechg"]
-            else:
-                data["subrun2"][i, :, :] += o["rechg"]
-        else:
-            data["rechg"][i, :, :] = o["rechg"]
     return data
+
+
+def post_process_output(output: dict, context=None, lat_dd=None, lon_dd=None) -> dict:
+    """The same for the dict of per-cell dicts :func:`run_help_allcells` returns (the argument
+    ``_post_process_output`` takes in the reference)."""
+    cellnames = list(output.keys())
+    monthly = np.stack([np.stack([output[c][k] for c in cellnames], axis=-1) for k in KEYS])
+    return post_process_monthly(monthly, output[cellnames[0]]["years"], cellnames, context, lat_dd, lon_dd)

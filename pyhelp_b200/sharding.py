@@ -21,12 +21,22 @@ def shard_range(n_cells: int, world: int, rank: int) -> tuple[int, int]:
     return start, start + base + (1 if rank < rem else 0)
 
 
+# Relative cost of a cell by profile structure, per modelling segment (calibrated on B200: per-rank
+# kernel times of class-sorted shards of BASELINE configs[2]/[3], profiles/r2_notes.md): a profile
+# with a liner pays head, leakage and lateral-drainage iterations every sub-step and runs more
+# sub-steps per day.
+COST_LINER = 3.0
+
+
+def _segments(nlay, thick_in, on):
+    """7 evaporative segments + 1..3 per layer by thickness (reference ``HELP3O.FOR:1503-1616``)."""
+    return 7 + np.where(on, np.clip(np.ceil(thick_in / 18.0), 1, 3), 0).sum(axis=0)
+
+
 def estimate_cost(batch: CellBatch) -> np.ndarray:
     """Relative simulation cost of every cell, from its layer records alone (no GPU work):
-    ~ number of modelling segments (7 evaporative + 1..3 per layer by thickness, reference
-    ``HELP3O.FOR:1503-1616``) times 3 for a profile with a liner (barrier soil or geomembrane:
-    head, leakage and lateral-drainage iterations every sub-step; measured on B200: a
-    drain-over-barrier cell costs ~3x, a double-liner landfill cover ~5x a natural-soil cell)."""
+    ~ number of modelling segments times :data:`COST_LINER` for a profile with a liner (barrier
+    soil or geomembrane)."""
     from . import _native as N
     nlay = batch.cell_i32[N.HB_NLAY].astype(np.int64)
     L = batch.max_layers
@@ -34,10 +44,61 @@ def estimate_cost(batch: CellBatch) -> np.ndarray:
     thick = batch.layer_f32[N.HL_THICK]                       # cm (IU10 = 2) or inches
     si = batch.cell_i32[N.HB_IU10] == 2
     inches = np.where(si[None, :], thick / 2.54, thick)
-    nseg = 7 + np.where(lay, np.clip(np.ceil(inches / 18.0), 1, 3), 0).sum(axis=0)
     ltype = batch.layer_i32[N.HL_TYPE]
     liner = (lay & (ltype >= 3)).any(axis=0)
-    return nseg * np.where(liner, 3.0, 1.0)
+    return _segments(nlay, inches, lay) * np.where(liner, COST_LINER, 1.0)
+
+
+def grid_cost_and_class(grid: dict):
+    """(cost, class) of every cell straight from the grid columns (``nlayer``, ``lay_type{i}``,
+    ``thick{i}`` in cm; docs/data.rst:122-188), before anything is packed.  ``class`` orders the
+    kernel instantiations a shard needs: segment capacity tier of the profile (<= 3 layers: 16
+    segments, <= 6: 25, <= 11: 40, else 67 -- the engine sizes its per-thread arrays by the deepest
+    profile of a batch) and, inside a tier, profiles without a liner first (they run the
+    plain-profile routing)."""
+    nlay = np.asarray(grid["nlayer"]).astype(np.int64)
+    n = nlay.size
+    L = int(nlay.max()) if n else 0
+    thick = np.zeros((max(L, 1), n))
+    ltype = np.zeros((max(L, 1), n), dtype=np.int64)
+    for j in range(L):
+        s = str(j + 1)
+        if "thick" + s in grid:
+            thick[j] = np.maximum(np.asarray(grid["thick" + s], dtype=float), 10.0)     # MINTHICK, preprocessing.py:22
+        if "lay_type" + s in grid:
+            ltype[j] = np.asarray(grid["lay_type" + s]).astype(np.int64)
+    on = np.arange(max(L, 1))[:, None] < nlay[None, :]
+    liner = (on & (ltype >= 3)).any(axis=0)
+    cost = _segments(nlay, thick / 2.54, on) * np.where(liner, COST_LINER, 1.0)
+    tier = np.digitize(nlay, [4, 7, 12])                     # 0: <=3 layers, 1: <=6, 2: <=11, 3: more
+    return cost, (2 * tier + liner.astype(np.int64))
+
+
+def plan_shards(cost, klass, world: int, node=None):
+    """Partition of one grid over ``world`` ranks: cells stably sorted by (class,
+    cost, weather node), the sorted list cut into contiguous runs of equal total cost.  Returns
+    ``(order, ranges)``: rank r simulates the cells ``order[ranges[r][0]:ranges[r][1]]``.  Ranks then
+    hold (nearly) one profile class each, so each engine picks the kernel instantiation of its own
+    shard, and every rank finishes at the same time although a liner profile costs several natural
+    ones."""
+    cost = np.asarray(cost, dtype=np.float64).reshape(-1)
+    keys = [np.zeros(cost.size, dtype=np.int64) if node is None else np.asarray(node).reshape(-1), cost,
+            np.asarray(klass).reshape(-1)]
+    order = np.lexsort(keys)                                  # last key is the primary one; stable
+    return order, cost_balanced_ranges(cost[order], world)
+
+
+def restore_order(gathered, order):
+    """Results gathered in shard order (``[..., n_total]`` along the last axis) back in the caller's
+    cell order -- the reference returns one dict keyed by cell (``pyhelp/processing.py:40-59``)."""
+    import torch
+    if isinstance(gathered, torch.Tensor):
+        out = torch.empty_like(gathered)
+        out[..., torch.as_tensor(np.asarray(order), device=gathered.device)] = gathered
+        return out
+    out = np.empty_like(gathered)
+    out[..., np.asarray(order)] = gathered
+    return out
 
 
 def cost_balanced_ranges(cost, world: int) -> list[tuple[int, int]]:

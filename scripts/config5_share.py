@@ -5,7 +5,8 @@ import os, sys, time
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from pyhelp_b200 import synth, grid as G, processing, _native as N
+from pyhelp_b200 import grid as G, processing, _native as N
+from support import synth
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 625000
 ny = int(sys.argv[2]) if len(sys.argv) > 2 else 30

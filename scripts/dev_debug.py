@@ -2,7 +2,8 @@ import os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from pyhelp_b200 import synth, inputs, processing
+from pyhelp_b200 import inputs, processing
+from support import synth
 from oracle import oracle
 np.set_printoptions(linewidth=200, precision=4, suppress=True)
 n, ny = 16, 2

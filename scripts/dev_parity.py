@@ -4,7 +4,8 @@ import os, sys, time, json
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from pyhelp_b200 import synth, grid as G, inputs, processing
+from pyhelp_b200 import grid as G, inputs, processing
+from support import synth
 from oracle import oracle
 
 def cmp(tag, gpu, orc, names):

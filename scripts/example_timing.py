@@ -9,7 +9,8 @@ import numpy as np
 import pandas as pd
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from pyhelp_b200 import managers, synth
+from pyhelp_b200 import managers
+from support import synth
 
 z = np.load(os.path.join(ROOT, "tests", "golden", "example_weather.npz"))
 idx = pd.DatetimeIndex(pd.to_datetime({"year": z["year"].astype(int), "month": z["month"].astype(int), "day": z["day"].astype(int)}), name="date")

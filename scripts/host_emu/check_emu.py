@@ -5,7 +5,8 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__)); ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT); sys.path.insert(0, HERE)
 subprocess.check_call("g++ -O2 -mfma -ffp-contract=off -std=c++17 -shared -fPIC %s emu.cpp -o libemu.so" % os.environ.get("EMU_FLAGS", ""), shell=True, cwd=HERE)
-from pyhelp_b200 import synth, inputs
+from pyhelp_b200 import inputs
+from support import synth
 from oracle import oracle
 import run_emu
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 48

@@ -28,6 +28,7 @@ static inline unsigned __ballot_sync(unsigned, int p) { return p ? 1u : 0u; }
 static inline int __any_sync(unsigned, int p) { return p; }
 static inline unsigned __activemask() { return 1u; }
 static inline void __syncthreads() {}
+static inline int __syncthreads_or(int p) { return p; }
 static inline float __fmul_rn(float a, float b) { return a * b; }
 static inline float __fadd_rn(float a, float b) { return a + b; }
 #include <math.h>

@@ -6,7 +6,8 @@ import ctypes as C, os, sys
 import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__)); ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
-from pyhelp_b200 import synth, grid as G, _native as N
+from pyhelp_b200 import grid as G, _native as N
+from support import synth
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
 ny = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 kind = sys.argv[3] if len(sys.argv) > 3 else "natural3"

@@ -67,6 +67,23 @@ def synth_weather(n_nodes: int, year0: int, n_years: int, seed: int, lat0: float
     }
 
 
+def synth_weather_chunked(n_nodes: int, year0: int, n_years: int, seed: int, chunk: int = 500, lat0: float = 46.0):
+    """:func:`synth_weather` for many nodes, generated `chunk` nodes at a time (seed + chunk index) so
+    that the temporaries stay small; the tables come out C-contiguous [day][node]."""
+    out = None
+    for c, a in enumerate(range(0, n_nodes, chunk)):
+        b = min(a + chunk, n_nodes)
+        w = synth_weather(b - a, year0, n_years, seed=seed * 7919 + c, lat0=lat0)
+        if out is None:
+            T = w["years_of_day"].size
+            out = {"years_of_day": w["years_of_day"], "lat": np.empty(n_nodes), "lon": np.empty(n_nodes),
+                   "precip": np.empty((T, n_nodes)), "airtemp": np.empty((T, n_nodes)), "solrad": np.empty((T, n_nodes))}
+        for k in ("precip", "airtemp", "solrad"):
+            out[k][:, a:b] = w[k]
+        out["lat"][a:b], out["lon"][a:b] = w["lat"], w["lon"]
+    return out
+
+
 # ---------------------------------------------------------------------------
 # grids
 # ---------------------------------------------------------------------------

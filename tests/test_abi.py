@@ -86,7 +86,8 @@ def test_no_cpu_fallback(lib):
     """Without a CUDA device every compute entry must fail loudly (ENODEV), never compute."""
     if lib.help_b200_device_count() > 0:
         pytest.skip("a CUDA device is visible")
-    from pyhelp_b200 import processing, synth, grid as G
+    from pyhelp_b200 import processing, grid as G
+    from support import synth
     g = synth.grid_natural_3layer(4, seed=1)
     wx = synth.synth_weather(1, 2001, 1, seed=1)
     node = np.zeros(4, np.int32)

@@ -8,7 +8,8 @@ import numpy as np
 import pytest
 
 from oracle import oracle
-from pyhelp_b200 import inputs, processing, synth
+from pyhelp_b200 import inputs, processing
+from support import synth
 from pyhelp_b200 import _native as N
 
 HERE = osp.dirname(osp.abspath(__file__))

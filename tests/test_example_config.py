@@ -13,7 +13,8 @@ import os.path as osp
 import numpy as np
 import pytest
 
-from pyhelp_b200 import managers, synth
+from pyhelp_b200 import managers, processing
+from support import synth
 from oracle import nodes_oracle, oracle, post_oracle
 
 GOLD = osp.join(osp.dirname(osp.abspath(__file__)), "golden", "example_weather.npz")
@@ -111,7 +112,7 @@ def test_post_process_monthly_equals_the_reference_loop():
     per_cell = {nm: dict(years=np.arange(2000, 2000 + ny, dtype=np.uint16),
                          **{k: monthly[r, :, :, i] for r, k in enumerate(rows)}) for i, nm in enumerate(names)}
     want = post_oracle.post_process_output(per_cell, context)
-    got = managers.post_process_monthly(monthly, np.arange(2000, 2000 + ny), names, context, np.zeros(n), np.zeros(n))
+    got = processing.post_process_monthly(monthly, np.arange(2000, 2000 + ny), names, context, np.zeros(n), np.zeros(n))
     for k in KEYS:
         assert got[k].dtype == np.float64 and got[k].shape == (n, ny, 12)
         assert np.array_equal(got[k], want[k], equal_nan=True), k

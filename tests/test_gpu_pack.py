@@ -1,0 +1,52 @@
+"""The host packer's device leg (`-m gpu`): help_b200_pack_weather (csrc/help_weather.cuh) must
+return the bits of the reference's text round trip -- float32(float(format(x, '.Nf'))) as
+pyhelp/weather_reader.py:31,44,57 prints and READCD (HELP3O.FOR:1100-1129) reads -- in the engine's
+[node][year][368] layout, i.e. exactly what grid.weather_to_nodes computes on the host."""
+import numpy as np
+import pytest
+
+from pyhelp_b200 import grid as G
+from support import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def test_device_weather_equals_host_weather():
+    wx = synth.synth_weather(70, 2003, 3, seed=9)                    # 2004 is a leap year; 70 nodes: ragged tiles
+    for key, d in (("precip", 1), ("airtemp", 1), ("solrad", 2)):
+        raw = wx[key] + np.random.default_rng(1).normal(0, 0.04, wx[key].shape)      # off the quantisation grid
+        yh, h = G.weather_to_nodes(wx["years_of_day"], raw, d, "host")
+        yd, dv = G.weather_to_nodes(wx["years_of_day"], raw, d, "device")
+        assert np.array_equal(yh, yd) and h.dtype == dv.dtype == np.float32 and h.shape == dv.shape == (70, 3, 368)
+        assert np.array_equal(h.view(np.uint32), dv.view(np.uint32))
+
+
+def test_device_quantisation_is_pythons_format_on_ties_and_near_ties():
+    """'{:.1f}'.format rounds the exact binary value half to even: 0.25 -> 0.2, 0.35 (just below in binary) -> 0.3,
+    0.75 -> 0.8, 2.675 -> 2.67 (binary below), 1.005 -> 1.00; products x*10^d that round onto a tie must not be
+    treated as one."""
+    base = np.array([0.25, 0.35, 0.75, 0.05, 0.15, 0.45, 2.5, 3.5, -0.25, -0.35, 1e-9, 123.45, 2.675, 1.005, 0.125, 0.375,
+                     1234.5678, 0.0, 65.55, 99.95])
+    rng = np.random.default_rng(3)
+    vals = np.concatenate([base, np.nextafter(base, 10), np.nextafter(base, -10), rng.integers(0, 4000, 325) / 8.0,
+                           rng.integers(-2000, 2000, 300) / 16.0 + 0.05])
+    vals = vals[:365].reshape(365, 1)
+    yod = np.full(365, 2001, dtype=np.int32)
+    for d in (0, 1, 2, 3):
+        want = np.array([float(format(x, f".{d}f")) for x in vals[:, 0]]).astype(np.float32)
+        _, got = G.weather_to_nodes(yod, vals, d, "device")
+        assert np.array_equal(got[0, 0, :365], want + np.float32(0.0)), d
+        assert (got[0, 0, 365:] == 0).all()
+        _, host = G.weather_to_nodes(yod, vals, d, "host")
+        assert np.array_equal(host[0, 0], got[0, 0])
+
+
+def test_batch_from_grid_device_weather_gives_the_same_batch():
+    n, nn, ny = 64, 5, 2
+    g = synth.grid_mixed(n, seed=2)
+    wx = synth.synth_weather(nn, 2001, ny, seed=5)
+    node = synth.assign_nodes(n, nn)
+    a = G.batch_from_grid(g, wx["years_of_day"], wx["precip"], wx["airtemp"], wx["solrad"], node, node, node, weather="host")
+    b = G.batch_from_grid(g, wx["years_of_day"], wx["precip"], wx["airtemp"], wx["solrad"], node, node, node, weather="device")
+    for k in ("years", "pre", "tmp", "rad", "idfs", "cell_f32", "cell_i32", "layer_f32", "layer_i32", "layer_rc"):
+        assert np.array_equal(getattr(a, k), getattr(b, k)), k

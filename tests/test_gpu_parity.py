@@ -13,7 +13,8 @@ import pytest
 
 from oracle import oracle
 from pyhelp_b200 import grid as G
-from pyhelp_b200 import inputs, processing, synth
+from pyhelp_b200 import inputs, processing
+from support import synth
 from pyhelp_b200 import _native as N
 
 pytestmark = pytest.mark.gpu

@@ -8,7 +8,8 @@ import numpy as np
 import pytest
 
 from pyhelp_b200 import grid as G
-from pyhelp_b200 import inputs, synth
+from pyhelp_b200 import inputs
+from support import synth
 from pyhelp_b200 import _native as N
 
 
@@ -106,3 +107,34 @@ def test_fixed_length_records_fast_path_equals_the_padded_path(tmp_path):
     g.write_bytes(b"\r\n".join(txt))
     b = inputs.read_weather_file(str(g), "D7")
     assert np.array_equal(a.data, b.data) and np.array_equal(a.years, b.years) and a.units == b.units
+
+
+def test_idfs_prescan_reads_f61_whatever_the_units(tmp_path):
+    """READIN's pre-scan of the D13 file uses F6.1 (formats 5400/5410, F:1364-1365) although READCD
+    reads SI radiation with F6.0 (F:1128): an SI file written without decimal points gives the
+    pre-scan values ten times smaller, hence another IDFS than the yearly data would.  The oracle
+    reads the file record by record like the Fortran; the vectorised host parser must agree."""
+    from oracle import oracle
+    wx = synth.synth_weather(1, 2001, 2, seed=3)
+    files = synth.write_weather_files(str(tmp_path), wx)
+    lines = open(files["D13"][0]).read().split("\n")
+    out = lines[:4]
+    for ln in lines[4:]:
+        if not ln:
+            continue
+        vals = [float(ln[5 + 6 * k:11 + 6 * k]) for k in range(10)]
+        out.append(ln[:5] + "".join("{0:>6d}".format(int(round(v))) for v in vals))       # integer MJ/m2, no point
+    p = tmp_path / "int.D13"
+    p.write_text("\n".join(out) + "\n")
+    plain = inputs.read_weather_file(files["D13"][0], "D13")
+    ints = inputs.read_weather_file(str(p), "D13")
+    assert np.array_equal(ints.data, np.rint(plain.data))                                  # READCD: F6.0
+    assert ints.idfs[0] > plain.idfs[0]                                                    # pre-scan saw a tenth of the radiation
+    g = synth.grid_natural_3layer(1, seed=1)
+    node = np.zeros(1, np.int32)
+    f2 = {"D4": files["D4"], "D7": files["D7"], "D13": {0: str(p)}}
+    cp = synth.cellparams_from_grid(g, f2, node, node, node, 2)
+    info = oracle.run_simulation(*cp["0"], full=True)["info"]
+    assert info["idfs"] == ints.idfs[0]
+    # Fw.d without a point: the implied decimals apply to the significand, exponent or not
+    assert inputs._to_real(np.array([b"125E1", b"12.5E1", b"125"]), 2, np.float64).tolist() == [12.5, 125.0, 1.25]

@@ -12,7 +12,7 @@ reference itself has the same spread between two machines with different libm ve
 import numpy as np
 
 from oracle import oracle
-from pyhelp_b200 import synth
+from support import synth
 
 
 def test_last_bit_of_libm_moves_yearly_totals(tmp_path):

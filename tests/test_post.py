@@ -31,7 +31,8 @@ def test_library_exports_entry_point():
 @pytest.mark.gpu
 @pytest.mark.parametrize("family,n,ny", [("natural3", 300, 3), ("mixed", 257, 2)])
 def test_gpu_reductions_match_oracle(family, n, ny):
-    from pyhelp_b200 import synth, grid as G, processing, _native as N
+    from pyhelp_b200 import grid as G, processing, _native as N
+    from support import synth
     res = {"natural3": synth.grid_natural_3layer, "mixed": synth.grid_mixed}[family](n, seed=21)
     g, ex = res if isinstance(res, tuple) else (res, None)
     wx = synth.synth_weather(3, 2001, ny, seed=4)

@@ -10,7 +10,8 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from pyhelp_b200 import grid as G
-from pyhelp_b200 import sharding, synth
+from pyhelp_b200 import sharding
+from support import synth
 from pyhelp_b200 import _native as N
 
 
@@ -99,7 +100,8 @@ def test_cost_balanced_ranges():
 
 
 def test_estimated_cost_ranks_liner_profiles_above_natural_soil():
-    from pyhelp_b200 import grid as G, synth
+    from pyhelp_b200 import grid as G
+    from support import synth
     n = 64
     g, ex = synth.grid_landfill(n, seed=3)
     wx = synth.synth_weather(2, 2001, 1, seed=1)
@@ -161,3 +163,66 @@ def test_run_batch_devices_joins_shards_in_caller_order(monkeypatch):
     monkeypatch.setattr(processing, "run_batch", boom)
     with pytest.raises(N.EngineError):
         processing.run_batch_devices(b, 2)
+
+
+def test_grid_plan_is_class_sorted_and_cost_balanced():
+    """sharding.grid_cost_and_class / plan_shards: one grid, class-sorted, cut into runs of equal cost
+     -- from the grid columns alone, and equal to the cost the packed batch gives."""
+    n, world = 4000, 4
+    g = synth.grid_mixed(n, seed=2)
+    node = synth.assign_nodes(n, 40)
+    cost, klass = sharding.grid_cost_and_class(g)
+    wx = synth.synth_weather(40, 2001, 1, seed=1)
+    b = G.batch_from_grid(g, wx["years_of_day"], wx["precip"], wx["airtemp"], wx["solrad"], node, node, node)
+    assert np.array_equal(cost, sharding.estimate_cost(b))
+    order, ranges = sharding.plan_shards(cost, klass, world, node)
+    assert np.array_equal(np.sort(order), np.arange(n))
+    assert ranges[0][0] == 0 and ranges[-1][1] == n and all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
+    assert (np.diff(klass[order]) >= 0).all()                              # class-major
+    tot = np.array([cost[order[a:b]].sum() for a, b in ranges])
+    assert tot.max() / tot.mean() < 1.01
+    # plain profiles of at most 16 segments first: the first rank needs only the narrow kernel instantiation
+    a, b_ = ranges[0]
+    lt = np.stack([g[f"lay_type{j}"] for j in range(1, 6)])
+    assert (lt[:, order[a:b_]] < 3).all() and g["nlayer"][order[a:b_]].max() <= 3
+    # liner profiles cost more, so their ranks hold fewer cells
+    assert (ranges[-1][1] - ranges[-1][0]) < (ranges[0][1] - ranges[0][0])
+    r = sharding.restore_order(np.arange(n, dtype=np.float32)[order][None, :], order)
+    assert np.array_equal(r[0], np.arange(n, dtype=np.float32))
+
+
+def _plan_worker(rank, world, port, n_total, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = synth.grid_mixed(n_total, seed=5)
+    node = synth.assign_nodes(n_total, 9)
+    cost, klass = sharding.grid_cost_and_class(g)
+    order, ranges = sharding.plan_shards(cost, klass, world, node)
+    a, b = ranges[rank]
+    idx = torch.as_tensor(order[a:b].astype(np.float32))                    # "result" of a cell = its caller index
+    y = idx[None, None, :] + 1000.0 * torch.arange(5)[:, None, None] + 10.0 * torch.arange(2)[None, :, None]
+    full = sharding.gather_yearly(y, n_total, world, rank, ranges=ranges)
+    if rank == 0:
+        q.put((sharding.restore_order(full, order).numpy(), ranges))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_planned_shards_gather_to_caller_order_gloo_world2():
+    """the N>1 path of bench.py's `target` on CPU: unequal, class-sorted shards, gathered over gloo and
+    put back in the caller's cell order"""
+    n_total = 301
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_plan_worker, args=(r, 2, port, n_total, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got, ranges = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert (ranges[0][1] - ranges[0][0]) != (ranges[1][1] - ranges[1][0])
+    want = (np.arange(n_total, dtype=np.float32)[None, None, :] + 1000.0 * np.arange(5)[:, None, None]
+            + 10.0 * np.arange(2)[None, :, None])
+    assert np.array_equal(got, want)
