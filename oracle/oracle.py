@@ -30,7 +30,8 @@ _HERE = osp.dirname(osp.abspath(__file__))
 # transcendentals of pyhelp_b200/csrc/help_math.h (the build the GPU engine must match
 # bit for bit), "glibc" the host libm a gfortran build of the reference would link.
 _LIB_PATHS = {"det": osp.join(_HERE, "libhelp3o_oracle.so"),
-              "glibc": osp.join(_HERE, "libhelp3o_oracle_glibc.so")}
+              "glibc": osp.join(_HERE, "libhelp3o_oracle_glibc.so"),
+              "glibc_noise": osp.join(_HERE, "libhelp3o_oracle_glibc_noise.so")}
 _LIB_PATH = _LIB_PATHS["det"]
 _libs = {}
 
@@ -154,11 +155,16 @@ def _run_single_glibc(item):
     return name, run_simulation(*p, libm="glibc")
 
 
+def _run_single_glibc_noise(item):
+    name, p = item
+    return name, run_simulation(*p, libm="glibc_noise")
+
+
 def run_help_allcells(cellparams: dict, ncore: int | None = None, libm: str = "det") -> dict:
     """Reference-shaped fan-out (pyhelp/processing.py:40-59) over the oracle."""
     ncore = max(mp.cpu_count() if ncore is None else ncore, 1)
     _load(libm)
-    fn = _run_single if libm == "det" else _run_single_glibc
+    fn = {"det": _run_single, "glibc": _run_single_glibc, "glibc_noise": _run_single_glibc_noise}[libm]
     if ncore == 1 or len(cellparams) < 2:
         return dict(fn(it) for it in cellparams.items())
     with mp.get_context("fork").Pool(ncore) as pool:

@@ -201,10 +201,11 @@ constexpr uint32_t kFlagNonConv = 0x1u, kFlagNaN = 0x2u, kFlagOverflow = 0x4u, k
 // ---- transcendental functions ------------------------------------------------------------
 // The reference's surface-process code is REAL*4 and its routing code REAL*8; both get
 // their transcendentals from libm.  HELP is chaotic in the last bit of those functions
-// (help_math.h), so the engine uses the deterministic implementations of help_math.h --
-// the same ones the CPU oracle is built with -- instead of CUDA's libdevice:
-//   r4_*(x): REAL*4 intrinsic = correctly rounded float (evaluated in double, rounded once)
-//   r8_*(x): REAL*8 intrinsic, < 1 ulp
+// (DESIGN.md section 4), so the engine does not use CUDA's libdevice: it runs the operation
+// sequences of the libm the reference links in this image (help_math_glibc.h: glibc 2.39,
+// x86-64, FMA variants), the same source the CPU oracle is built from:
+//   r4_*(x): REAL*4 intrinsic = glibc's expf/logf/log10f/sinf/cosf/tanf/acosf/powf, bit for bit
+//   r8_*(x): REAL*8 intrinsic = glibc's pow/log/sin/cos/atan, bit for bit (sqrt: IEEE)
 #ifndef HELP_R4_OVERRIDE   // (scripts/host_emu swaps in glibc's libm to separate logic from libm differences)
 using helpmath::r4_exp; using helpmath::r4_log; using helpmath::r4_log10; using helpmath::r4_sin;
 using helpmath::r4_cos; using helpmath::r4_tan; using helpmath::r4_acos; using helpmath::r4_pow;
@@ -223,9 +224,9 @@ __host__ __device__ __forceinline__ double r8_pow_logbase(double x, double hi, d
   return helpmath::det_pow_logbase(x, hi, lo, y);   // x**y, same bits as r8_pow, logarithm of x supplied
 }
 __host__ __device__ __forceinline__ double r8_log(double x) { return helpmath::det_log(x); }
-__host__ __device__ __forceinline__ double r8_atan(double x) { return helpmath::det_atan(x); }
-__host__ __device__ __forceinline__ double r8_sin(double x) { return helpmath::det_sin(x); }
-__host__ __device__ __forceinline__ double r8_cos(double x) { return helpmath::det_cos(x); }
+__host__ __device__ __forceinline__ double r8_atan(double x) { return helpmath::g_atan(x); }
+__host__ __device__ __forceinline__ double r8_sin(double x) { return helpmath::g_sin(x); }
+__host__ __device__ __forceinline__ double r8_cos(double x) { return helpmath::g_cos(x); }
 __host__ __device__ __forceinline__ double r8_sqrt(double x) { return helpmath::hm_sqrt(x); }
 #endif
 

@@ -72,9 +72,9 @@ using helpmath::r4_sqrt; using helpmath::r4_pow8; using helpmath::r4_pow7; using
 static inline double r8_log(double x) { return helpmath::det_log(x); }
 static inline void r8_log_pair(double x, double& hi, double& lo) { helpmath::det_log_pair(x, hi, lo); }
 static inline double r8_pow_logbase(double x, double hi, double lo, double y) { return helpmath::det_pow_logbase(x, hi, lo, y); }
-static inline double r8_atan(double x) { return helpmath::det_atan(x); }
-static inline double r8_sin(double x) { return helpmath::det_sin(x); }
-static inline double r8_cos(double x) { return helpmath::det_cos(x); }
+static inline double r8_atan(double x) { return helpmath::g_atan(x); }
+static inline double r8_sin(double x) { return helpmath::g_sin(x); }
+static inline double r8_cos(double x) { return helpmath::g_cos(x); }
 static inline double r8_sqrt(double x) { return helpmath::hm_sqrt(x); }
 }
 static long long g_cap[8]; static float g_prev_relsw[128];
@@ -107,9 +107,9 @@ using helpmath::r4_sqrt; using helpmath::r4_pow8; using helpmath::r4_pow7; using
 static inline double r8_log(double x) { return helpmath::det_log(x); }
 static inline void r8_log_pair(double x, double& hi, double& lo) { helpmath::det_log_pair(x, hi, lo); }
 static inline double r8_pow_logbase(double x, double hi, double lo, double y) { return helpmath::det_pow_logbase(x, hi, lo, y); }
-static inline double r8_atan(double x) { return helpmath::det_atan(x); }
-static inline double r8_sin(double x) { return helpmath::det_sin(x); }
-static inline double r8_cos(double x) { return helpmath::det_cos(x); }
+static inline double r8_atan(double x) { return helpmath::g_atan(x); }
+static inline double r8_sin(double x) { return helpmath::g_sin(x); }
+static inline double r8_cos(double x) { return helpmath::g_cos(x); }
 static inline double r8_sqrt(double x) { return helpmath::hm_sqrt(x); }
 static inline double r8_pow(double x, double y) { g_np++; return helpmath::det_pow(x, y); }
 static inline void r8_pow2(double x0, double y0, double x1, double y1, double& r0, double& r1) { g_np += 2; auto R = helpmath::det_pow2(x0, y0, x1, y1); r0 = R.a; r1 = R.b; }
