@@ -81,6 +81,7 @@ enum ImgSD : int {
   SD_BC,         // B = K dt (1/(UL-RS))**C of the Newton solve     (F:4466)
   SD_LOWWP,      // LOW = K dt ((WP-RS)/(UL-RS))**C, i.e. SWLIM = WP (F:4420)
   SD_LOWFC,      // LOW at SWLIM = FC
+  SD_SUBIN,      // DSUBIN   subsurface inflow, in/day, REAL*8: the inflow of a liner is ADDED to the segment above it in REAL*8 (F:2060-2071)
   SD_NF
 };
 // ---- f64 per subprofile ---------------------------------------------------------

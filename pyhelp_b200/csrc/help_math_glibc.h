@@ -61,8 +61,9 @@ static __device__ const double kGAtanCijDev[241 * 7] = HG_ATAN_CIJ;
 // immediate base instead of a global load with its descriptor set-up (profiles/r1_notes.md).
 __shared__ LogEnt s_hmLogTab[128];
 __shared__ GExpEntBits s_hmExpTab[128];
+__shared__ GF2 s_hmLog2Tab[128];                           // log()'s own table (2 KB): geomembrane leakage takes logarithms every sub-step
 static __device__ __forceinline__ void hm_load_tables() {
-  for (int i = threadIdx.x; i < 128; i += blockDim.x) { s_hmLogTab[i] = kGPowLogDev[i]; s_hmExpTab[i] = kGExpDev[i]; }
+  for (int i = threadIdx.x; i < 128; i += blockDim.x) { s_hmLogTab[i] = kGPowLogDev[i]; s_hmExpTab[i] = kGExpDev[i]; s_hmLog2Tab[i] = kGLogDev[i]; }
   __syncthreads();
 }
 #define HG_SHARED 1
@@ -74,12 +75,15 @@ static inline void hm_load_tables() {}
 #if defined(__CUDA_ARCH__) && defined(HG_SHARED)
 #define HG_POWLOG(i) s_hmLogTab[i]
 #define HG_EXPT(i) s_hmExpTab[i]
+#define HG_LOGT(i) s_hmLog2Tab[i]
 #elif defined(__CUDA_ARCH__)
 #define HG_POWLOG(i) kGPowLogDev[i]
 #define HG_EXPT(i) kGExpDev[i]
+#define HG_LOGT(i) kGLogDev[i]
 #else
 #define HG_POWLOG(i) kGPowLogHost[i]
 #define HG_EXPT(i) kGExpHost[i]
+#define HG_LOGT(i) kGLogHost[i]
 #endif
 #if defined(__CUDA_ARCH__)
 #define HG_EXP2F(i) kGExp2fDev[i]
@@ -87,7 +91,6 @@ static inline void hm_load_tables() {}
 #define HG_POWFLOG2(i) kGPowfLog2Dev[i]
 #define HG_SINCOSF(k, j) kGSinCosfDev[k][j]
 #define HG_INVPIO4(i) kGInvPio4Dev[i]
-#define HG_LOGT(i) kGLogDev[i]
 #define HG_SCT(i) kGSinCosDev[i]
 #define HG_CIJ(i, j) kGAtanCijDev[(i) * 7 + (j)]
 #else
@@ -96,7 +99,6 @@ static inline void hm_load_tables() {}
 #define HG_POWFLOG2(i) kGPowfLog2Host[i]
 #define HG_SINCOSF(k, j) kGSinCosfHost[k][j]
 #define HG_INVPIO4(i) kGInvPio4Host[i]
-#define HG_LOGT(i) kGLogHost[i]
 #define HG_SCT(i) kGSinCosHost[i]
 #define HG_CIJ(i, j) kGAtanCijHost[(i) * 7 + (j)]
 #endif
@@ -331,10 +333,9 @@ HM_NOINLINE Pair det_pow_samebase(double x, double y0, double y1) {
 HM_NOINLINE double det_log(double x) {
   const double A[5] = HG_LOG_A;
   const double B[11] = HG_LOG_B;
-  uint64_t ix = as_u64(x);
-  const uint32_t top = (uint32_t)(ix >> 48);
-  if (ix - 0x3fee000000000000ull < 0x3090000000000ull) {   // 1 - 2^-4 <= x < 1 + 0x1.09p-4
-    if (ix == as_u64(1.0)) return 0.0;
+  uint32_t ixh = hi32(x), ixl = lo32(x);                  // (32-bit words: the GPU's registers)
+  if (ixh - 0x3fee0000u < 0x30900u) {                      // 1 - 2^-4 <= x < 1 + 0x1.09p-4
+    if (ixh == 0x3ff00000u && ixl == 0) return 0.0;
     const double r = hm_add(x, -1.0);
     const double r2 = hm_mul(r, r);
     const double r3 = hm_mul(r, r2);
@@ -353,20 +354,21 @@ HM_NOINLINE double det_log(double x) {
     const double y = hm_fma(q, r3, lo);
     return hm_add(hi, y);
   }
+  const uint32_t top = ixh >> 16;
   if (top - 0x0010u >= 0x7ff0u - 0x0010u) {                 // x < 2^-1022, inf or nan
-    if (ix * 2 == 0) return -hm_inf();
-    if (ix == as_u64(hm_inf())) return x;
+    if (((ixh << 1) | ixl) == 0) return -hm_inf();
+    if (ixh == 0x7ff00000u && ixl == 0) return x;
     if ((top & 0x8000u) || (top & 0x7ff0u) == 0x7ff0u) return hm_nan();
-    ix = as_u64(hm_mul(x, 0x1p52));
-    ix -= 52ull << 52;
+    const double xs = hm_mul(x, 0x1p52);                    // subnormal: normalise, the exponent field goes negative
+    ixh = hi32(xs) - (52u << 20); ixl = lo32(xs);
   }
-  const uint64_t tmp = ix - 0x3fe6000000000000ull;
-  const int i = (int)((tmp >> 45) & 127u);
-  const int k = (int)((int64_t)tmp >> 52);
-  const double z = as_f64(ix - (tmp & (0xfffull << 52)));
+  const uint32_t tmp = ixh - 0x3fe60000u;                   // OFF = 0x3fe6000000000000
+  const int i = (int)((tmp >> 13) & 127u);
+  const int k = (int32_t)tmp >> 20;
+  const double z = from_words(ixh - (tmp & 0xfff00000u), ixl);
   const GF2 e = HG_LOGT(i);
   const double r = hm_fma(z, e.invc, -1.0);
-  const double kd = (double)k;
+  const double kd = hm_add(from_words(0x43300000u, (uint32_t)k ^ 0x80000000u), -4503601774854144.0);   // (double)k
   const double w = hm_fma(kd, HG_LOG_LN2HI, e.logc);
   const double hi = hm_add(r, w);
   const double lo = hm_fma(kd, HG_LOG_LN2LO, hm_add(hm_add(w, -hi), r));

@@ -188,7 +188,7 @@ struct CellIn {
 
 // Returns false for a design this engine refuses (flagged, outputs NaN).
 __device__ inline bool discretise(Layers& L, Topo& T, Segs& S, CellIn& C, float& SUBINF, float& SEDEP,
-                                  float& OLDSNO, float* DSUBINd, int segcap) {   // F:1406-2311
+                                  float& OLDSNO, double* DSUBINd, int segcap) {   // F:1406-2311
   const float WF[8] = {0, 0.085f, 0.334f, 0.252f, 0.151f, 0.091f, 0.054f, 0.033f};
   for (int n = 0; n < 7; ++n) S.NSEGn[n] = 0;
   for (int n = 0; n < 8; ++n) T.LCASE[n] = 0;
@@ -460,7 +460,7 @@ help_setup_kernel(BatchDev B, Image img, const int32_t* __restrict__ perm, uint3
   const int64_t n = B.n_cells;
   Layers L; Segs S; Topo T; CellIn C;
   int LRIN[22];
-  float DSUBINd[70];
+  double DSUBINd[70];
   // ---- gather this cell's records (READIN, F:1221-1300) ------------------------------
   C.ULAT = B.cell_f32[HB_ULAT * n + c]; C.ULAI = B.cell_f32[HB_ULAI * n + c];
   C.EDEPTH = B.cell_f32[HB_EDEPTH * n + c]; C.WIND = B.cell_f32[HB_WIND * n + c];
@@ -621,7 +621,7 @@ help_setup_kernel(BatchDev B, Image img, const int32_t* __restrict__ perm, uint3
         if (N <= 5 && T.LD[N] > 0) lat = 1;
         if (lat == 1) { const int layd = S.LAYSEG2[NSEGL]; slope = L.SLOPE[layd]; xleng = L.XLENG[layd]; }
       }
-      drculs = S.RCUL[NSEGE]; dthics = S.STHICK[NSEGE]; sublin = DSUBINd[NSEGE];
+      drculs = S.RCUL[NSEGE]; dthics = S.STHICK[NSEGE]; sublin = (float)DSUBINd[NSEGE];
       if (S.NSEG == NSEGE) {                                            // F:4201-4210
         const int lp = T.LP[N];
         if (ibar == 1) { if (L.SUBIN[lp] > 0.0f) ibar += 3; }
@@ -660,7 +660,8 @@ help_setup_kernel(BatchDev B, Image img, const int32_t* __restrict__ perm, uint3
     img.SF(S_FC, J, slot) = in ? S.FCUL[J] : 0.f;      img.SF(S_WP, J, slot) = in ? S.WPUL[J] : 0.f;
     img.SF(S_RS, J, slot) = in ? S.RSUL[J] : 0.f;      img.SF(S_LAM, J, slot) = in ? S.XLAMBU[J] : 1.f;
     img.SF(S_BUB, J, slot) = in ? S.BUBUL[J] : 0.f;    img.SF(S_RC, J, slot) = in ? S.RCUL[J] : 0.f;
-    img.SF(S_SUBIN, J, slot) = in ? DSUBINd[J] : 0.f;  img.SF(S_SW0, J, slot) = in ? S.SWUL[J] : 0.f;
+    img.SF(S_SUBIN, J, slot) = in ? (float)DSUBINd[J] : 0.f;  img.SF(S_SW0, J, slot) = in ? S.SWUL[J] : 0.f;
+    img.SD(SD_SUBIN, J, slot) = in ? DSUBINd[J] : 0.0;
     if (!in) img.SI(J, slot) = 0;
   }
   // ---- routing-loop constants per segment (help_image.h ImgSD; F:4329, 4420, 4465-4466) -------------

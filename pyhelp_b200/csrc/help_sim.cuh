@@ -340,7 +340,7 @@ __device__ __noinline__ RouteOut route_subprofile(const Image& img, int64_t s, c
       const double rspan = Cv.x, kdt = Cv.y;
       const double span = ul - rs;
       const double Ej = (J <= 7) ? Ed[J] : 0.0;
-      const double DSUBj = has_sub ? (double)rec_tail(p).subin * DT : 0.0;
+      const double DSUBj = has_sub ? img.SD(SD_SUBIN, J, s) * DT : 0.0;      // (REAL*8: not in the routing records; rare)
       const double DRCRj = has_rcr ? SS.DRCRS[J] * DT : 0.0;            // DRCR(J) (F:4195)
       // lower storage limit SWLIM and the drainage LOW at that limit; kind: 0 capillary
       // equilibrium with the segment below, 1 wilting point, 2 field capacity, 3 porosity
@@ -487,7 +487,7 @@ __device__ __noinline__ RouteOut route_subprofile(const Image& img, int64_t s, c
         if (out > kdt1) {
           const RecTail t0 = rec_tail(p), t1 = rec_tail(p + kRecBytes);
           const double th = (double)t0.thick, th1 = (double)t1.thick;
-          const double ul1 = (double)A1.x, sub1 = (double)t1.subin;
+          const double ul1 = (double)A1.x, sub1 = has_sub ? img.SD(SD_SUBIN, J + 1, s) : 0.0;
           const float sw = (float)fdiv_by(base - rs, span, rspan);
           const float TRATIO = (float)(th / th1);
           const double En = (J + 1 <= 7) ? Ed[J + 1] : 0.0;
@@ -515,7 +515,7 @@ __device__ __noinline__ RouteOut route_subprofile(const Image& img, int64_t s, c
       { const double2 sb = SS.SB[NSEGL]; swk = sb.x; balk = sb.y; }
       float ulf = rec_f4<RV_A>(pk).x;
       for (int Kk = NSEGL; Kk >= NSEGB; --Kk) {
-        const double sub = has_sub ? (double)rec_tail(pk).subin * DT : 0.0;
+        const double sub = has_sub ? img.SD(SD_SUBIN, Kk, s) * DT : 0.0;
         // the loads of the next segment up, ahead of their use; unconditional (Kk-1 >= 0 is a
         // valid index of SB and DRIN, the record pointer stays on the top segment)
         if (Kk > NSEGB) pk -= kRecBytes;

@@ -109,7 +109,7 @@ def batch_from_grid(grid: dict, years_of_day, precip, airtemp, solrad, node_p, n
     lay_type{i}, thick{i}, poro{i}, fc{i}, wp{i}, ksat{i}, dist_dr{i}, slope{i}).
     ``precip``/``airtemp``/``solrad``: [day][node] tables in mm, deg C, MJ/m2/day.
     ``extra_layers``: optional per-layer design fields PyHELP's formatter leaves blank
-    (phole{i}, defec{i}, ipq{i}, trans{i}, recir{i}, layr{i}, subin{i}) for landfill designs.
+    (phole{i}, defec{i}, ipq{i}, trans{i}, recir{i}, layr{i}, subin{i}, sw{i}; per cell: ipre, osno) for landfill designs.
     ``weather``: ``"host"`` or ``"device"`` -- where the weather tables are quantised and laid out
     (:func:`weather_to_nodes`).
     Cells PyHELP would skip (nlayer == 0 or a -9999 layer field,
@@ -139,6 +139,10 @@ def batch_from_grid(grid: dict, years_of_day, precip, airtemp, solrad, node_p, n
     cell_f32[N.HB_FRUNOF] = 100.0
     cell_f32[N.HB_CN2] = quantize(g["CN"].astype(float) * sf_cn, 0)
     cell_f32[N.HB_TFSOIL] = F32((tfsoil_c * 1.8) + 32)          # managers.py:387
+    if extra_layers and "ipre" in extra_layers:            # user-specified initial moisture and snow (D10 record 2)
+        cell_i32[N.HB_IPRE] = np.asarray(extra_layers["ipre"], dtype=np.int32)
+    if extra_layers and "osno" in extra_layers:
+        cell_f32[N.HB_OSNO] = np.asarray(extra_layers["osno"], dtype=float)
     cell_i32[N.HB_NLAY] = nlay
     cell_i32[N.HB_NODE_P] = np.asarray(node_p, dtype=np.int32)
     cell_i32[N.HB_NODE_T] = np.asarray(node_t, dtype=np.int32)
@@ -169,10 +173,12 @@ def batch_from_grid(grid: dict, years_of_day, precip, airtemp, solrad, node_p, n
             layer_f32[N.HL_TRANS, j] = col("trans")
             layer_f32[N.HL_RECIR, j] = col("recir")
             layer_f32[N.HL_SUBIN, j] = col("subin")
+            layer_f32[N.HL_SW, j] = col("sw")
             layer_i32[N.HL_IPQ, j] = col("ipq").astype(np.int32)
             layer_i32[N.HL_LAYR, j] = col("layr").astype(np.int32)
             if f"thick_exact{s}" in ex:          # landfill liners are thinner than MINTHICK
-                layer_f32[N.HL_THICK, j] = np.where(on, np.asarray(ex[f"thick_exact{s}"], dtype=float), 0)
+                te = np.asarray(ex[f"thick_exact{s}"], dtype=float)
+                layer_f32[N.HL_THICK, j] = np.where(on & (te > 0), te, layer_f32[N.HL_THICK, j])
     years, pre = weather_to_nodes(years_of_day, precip, 1, weather)
     _, tmp = weather_to_nodes(years_of_day, airtemp, 1, weather)
     _, rad = weather_to_nodes(years_of_day, solrad, 2, weather)

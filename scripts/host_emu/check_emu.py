@@ -30,7 +30,8 @@ d10 = np.char.ljust(open(R + "RCRA.D10").read().splitlines(), 80).astype("S80")
 d11 = np.char.ljust(open(R + "RCRA.D11").read().splitlines(), 80).astype("S80")
 bad = 0 if ONLY else check("rcra", {"rcra": (R + "RCRA.D4", R + "RCRA.D7", R + "RCRA.D13", d11, d10, "/tmp/x.OUT", 0, 1, 0, 0, 3, 32.0)})
 for name, maker in (("natural3", synth.grid_natural_3layer), ("mixed", synth.grid_mixed), ("landfill", synth.grid_landfill),
-                    ("recirc", lambda n, seed: synth.grid_landfill(n, seed=seed, recirc=True)), ("deep", synth.grid_deep)):
+                    ("recirc", lambda n, seed: synth.grid_landfill(n, seed=seed, recirc=True)), ("deep", synth.grid_deep),
+                    ("special", synth.grid_special)):
     if ONLY and name != ONLY: continue
     res = maker(n, seed=11); g, ex = res if isinstance(res, tuple) else (res, None)
     nn = max(2, n // 16)

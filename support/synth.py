@@ -249,6 +249,60 @@ def grid_landfill(n: int, seed: int = 3, recirc: bool = False):
     return g, ex
 
 
+def grid_special(n: int, seed: int = 8):
+    """Branches of the reference no PyHELP grid reaches: geomembranes on a geotextile cushion
+    (placement quality 6 + transmissivity: FML design cases 5/6, ``HELP3O.FOR:5177-5285``), placement qualities
+    1 (perfect contact) and 5 (worst), subsurface inflow into the bottom subprofile with and without a liner
+    (IBAR 3/4/5, ``HELP3O.FOR:4164-4210``), user-specified initial moisture (IPRE = 1, ``HELP3O.FOR:986-996``,
+    snow water given), and sites at 55 / 65 deg N and 35 deg S (the HYDRO-17 melt-factor branches of SNOW,
+    ``HELP3O.FOR:3756-4122``, the June radiation block of the IDFS pre-scan and a growing season that wraps
+    around the new year).  Returns (grid, extra_layers)."""
+    rng = np.random.default_rng(seed)
+    g = _base_grid(n, rng)
+    var = np.arange(n) % 8
+    lat = np.array([55.3, 65.1, -35.2, 46.0, -35.2, 61.7, 52.4, 46.0])[np.arange(n) % 8 if n < 8 else rng.integers(0, 8, n)]
+    g["lat_dd"] = lat
+    south = lat < 0
+    g["growth_start"] = np.where(south, rng.integers(270, 300, n), g["growth_start"])
+    g["growth_end"] = np.where(south, rng.integers(100, 130, n), g["growth_end"])
+    # layer sequences: 0, 2, 3: topsoil / drain / geomembrane / clay; 1: topsoil / drain / clay / geomembrane (the
+    # geomembrane UNDER its controlling soil: design case 4, 6 with a geotextile); 4: topsoil / drain / clay (barrier
+    # soil liner); 5-7: three natural-soil layers
+    seqs = {0: [1, 2, 4, 3], 1: [1, 2, 3, 4], 2: [1, 2, 4, 3], 3: [1, 2, 4, 3], 4: [1, 2, 3, 0]}
+    g["nlayer"] = np.select([var < 4, var == 4], [4, 3], default=3)
+    ex = {"ipre": np.where(var >= 6, 1, 0)}
+    for j in range(1, 5):
+        s_ = str(j)
+        on = g["nlayer"] >= j
+        _soil_layer(g, j, n, rng, 1, on=on)
+        t = np.ones(n, dtype=int)
+        for v, sq in seqs.items():
+            t[var == v] = sq[j - 1]
+        t = np.where(on, t, 0)
+        g["lay_type" + s_] = t
+        drain, fml, clay = t == 2, t == 4, t == 3
+        g["thick" + s_] = np.where(drain, rng.integers(20, 46, n), np.where(clay, rng.integers(30, 91, n), g["thick" + s_])).astype(float)
+        for name, dv, cv in (("poro", 0.417, 0.427), ("fc", 0.045, 0.418), ("wp", 0.018, 0.367)):
+            g[name + s_] = np.where(drain, dv, np.where(clay, cv, np.where(fml, 0.0, g[name + s_])))
+        g["ksat" + s_] = np.where(drain, np.round(10 ** rng.uniform(-2.5, -1.0, n), 14), g["ksat" + s_])
+        g["ksat" + s_] = np.where(clay, np.round(10 ** rng.uniform(-7.0, -6.0, n), 14), g["ksat" + s_])
+        g["ksat" + s_] = np.where(fml, np.round(rng.uniform(2e-13, 4e-13, n), 14), g["ksat" + s_])
+        ex["thick_exact" + s_] = np.where(fml, np.round(rng.uniform(0.10, 0.15, n), 2), 0)
+        ex["phole" + s_] = np.where(fml, rng.integers(0, 3, n), 0).astype(float)
+        ex["defec" + s_] = np.where(fml, rng.integers(1, 11, n), 0).astype(float)
+        ex["ipq" + s_] = np.where(fml, np.select([var <= 1, var == 2], [6, np.where((np.arange(n) // 8) % 2 == 0, 1, 5)],
+                                                 default=rng.integers(2, 5, n)), 0)
+        ex["trans" + s_] = np.where(fml & (var <= 1), np.round(10 ** rng.uniform(-1.0, 1.0, n), 3), 0.0)
+        # subsurface inflow (mm/yr) into the bottom layer: the barrier soil under a geomembrane (3: IBAR 2 -> 5), a barrier
+        # soil liner (4: IBAR 1 -> 4), the last natural layer (5: added to the segment above in REAL*8, F:2060)
+        last = on & (g["nlayer"] == j)
+        ex["subin" + s_] = np.where(last & np.isin(var, (3, 4, 5)), rng.integers(20, 200, n), 0).astype(float)
+        sw = np.round(g["wp" + s_] + rng.uniform(0.2, 0.9, n) * (g["poro" + s_] - g["wp" + s_]), 3)
+        ex["sw" + s_] = np.where(on & (var >= 6) & ~fml, sw, 0.0)
+    ex["osno"] = np.where(var == 7, np.round(rng.uniform(5, 60, n), 0), 0.0)          # initial snow water, mm
+    return g, ex
+
+
 def grid_deep(n: int, seed: int = 6):
     """The largest profiles HELP accepts (HELP3O.FOR COMMON blocks: 20 layers, 67 segments): 12, 16
     or 20 layers, thick ones (3 segments each), natural soil with up to three drain-over-barrier
@@ -330,11 +384,13 @@ def format_d11(g: dict, i: int, sf_edepth=1.0, sf_ulai=1.0) -> list:
 
 def format_d10(g: dict, i: int, sf_cn=1.0, ex: dict | None = None) -> list:
     """preprocessing.py:79-185 for cell i (plus the optional liner fields for landfill designs)."""
+    ex = ex or {}
+    ipre = int(ex["ipre"][i]) if "ipre" in ex else 0
+    osno = float(ex["osno"][i]) if "osno" in ex else 0.0
     out = ["{0:<60}".format(str(g["cid"][i])),
-           "{0:>2}".format(2) + "{0:>2}".format(0) + "{0:>10.0f}".format(0) + "{0:>10.0f}".format(1) +
+           "{0:>2}".format(2) + "{0:>2}".format(ipre) + "{0:>10.0f}".format(osno) + "{0:>10.0f}".format(1) +
            "{0:>6.0f}".format(100) + "{0:>2}".format(1),
            "{0:>7.0f}".format(float(g["CN"][i]) * sf_cn)]
-    ex = ex or {}
     for j in range(int(g["nlayer"][i])):
         s = str(j + 1)
         thick = max(float(g["thick" + s][i]), 10)
@@ -343,7 +399,8 @@ def format_d10(g: dict, i: int, sf_cn=1.0, ex: dict | None = None) -> list:
             thick_txt = "{0:>7.2f}".format(float(ex["thick_exact" + s][i]))
         out.append("{0:>2}".format(int(g["lay_type" + s][i])) + thick_txt + "{0:>4}".format(0) +
                    "{0:>6.3f}".format(float(g["poro" + s][i])) + "{0:>6.3f}".format(float(g["fc" + s][i])) +
-                   "{0:>6.3f}".format(float(g["wp" + s][i])) + "{0:>6}".format("") +
+                   "{0:>6.3f}".format(float(g["wp" + s][i])) +
+                   ("{0:>6.3f}".format(float(ex["sw" + s][i])) if "sw" + s in ex and float(ex["sw" + s][i]) > 0 else "{0:>6}".format("")) +
                    "{0:>16.14f}".format(float(g["ksat" + s][i])))
         def opt(name, fmt, blank_w):
             if name + s in ex:
@@ -351,9 +408,9 @@ def format_d10(g: dict, i: int, sf_cn=1.0, ex: dict | None = None) -> list:
             return " " * blank_w
         out.append("{0:>7.0f}".format(float(g["dist_dr" + s][i])) + "{0:>6.2f}".format(float(g["slope" + s][i])) +
                    opt("recir", "{0:>6.0f}", 6) + ("{0:>3d}".format(int(ex["layr" + s][i])) if "layr" + s in ex else "{0:>3}".format(0)) +
-                   "{0:>13}".format("") +
+                   opt("subin", "{0:>13.2f}", 13) +
                    opt("phole", "{0:>7.0f}", 7) + opt("defec", "{0:>7.0f}", 7) + opt("ipq", "{0:>2d}", 2) +
-                   "{0:>14}".format(""))
+                   opt("trans", "{0:>14.6g}", 14))
     return out
 
 

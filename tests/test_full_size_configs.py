@@ -78,3 +78,40 @@ def test_landfill_covers_one_gpu_share_of_config_4(tmp_path):
     """250 000 landfill covers x 50 yr (topsoil / lateral-drainage layer / geomembrane / barrier
     soil) -> 31 250 cells here."""
     _run_and_check(tmp_path, "landfill", 31_250, 50, 12, seed=3)
+
+
+def test_province_scale_share_of_config_4_yearly_only(tmp_path):
+    """BASELINE configs[4]: 5 M cells x 30 yr, mixed classes, one weather node per 100 cells, yearly summaries only
+    (no 50 GB of monthly arrays) -> one GPU's eighth, 625 000 cells, with a monthly-free engine.  Properties on every
+    cell + sampled cells on the oracle (yearly rows = sums of the oracle's months)."""
+    n, ny = 625_000, 30
+    nn = n // 100
+    g = synth.grid_mixed(n, seed=4)
+    wx = synth.synth_weather_chunked(nn, 2001, ny, seed=4, chunk=625)
+    node = synth.assign_nodes(n, nn)
+    b = G.batch_from_grid(g, wx["years_of_day"], wx["precip"], wx["airtemp"], wx["solrad"], node, node, node, tfsoil_c=-3.0,
+                          weather="device")
+    with processing.HelpEngine(b, monthly=False) as eng:
+        eng.simulate()
+        r = eng.fetch(monthly=False, yearly=True)
+    y = r["yearly"]
+    assert y.shape == (N.HY_NROWS, ny, n) and "monthly" not in r
+    assert (r["flags"] & (N.FLAG_NAN | N.FLAG_BADCELL | N.FLAG_OVERFLOW)).sum() == 0
+    assert np.isfinite(y).all() and (y >= 0).all()
+    P, R, E, D, Q = (y[i].sum(axis=0).astype(np.float64) for i in range(5))
+    resid = (P - R - E - D - Q) / ny
+    assert np.abs(resid).max() < 80.0 and abs(resid.mean()) < 5.0, (np.abs(resid).max(), resid.mean())
+    sel = np.sort(np.random.default_rng(4).choice(n, 24, replace=False))
+    files = synth.write_weather_files(str(tmp_path), wx, nodes=sorted({int(node[i]) for i in sel}))
+    cp = synth.cellparams_from_grid(g, files, node, node, node, ny, tfsoil_c=-3.0, cells=sel.tolist())
+    want = oracle.run_help_allcells(cp)
+    for k, c in enumerate(sel.tolist()):
+        w = want[str(c)]
+        rows = (w["precip"], w["runoff"], w["evapo"], w["subrun1"] + w["subrun2"], w["rechg"])
+        for i, m in enumerate(rows):
+            # the engine sums the 12 float32 months of a year in order; so does this
+            s = np.zeros(ny, dtype=np.float32)
+            mm = m if i != 3 else None
+            for mo in range(12):
+                s = s + (m[:, mo] if i != 3 else (w["subrun1"][:, mo] + w["subrun2"][:, mo]))
+            assert np.array_equal(y[i, :, c], s), (c, i)

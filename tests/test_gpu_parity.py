@@ -57,12 +57,17 @@ def test_rcra_known_answers_and_bits(rcra_dir):
 
 
 @pytest.mark.parametrize("family,n,ny", [("natural3", 160, 3), ("mixed", 160, 3), ("landfill", 96, 3), ("recirc", 96, 3),
-                                         ("deep", 96, 2)])
+                                         ("deep", 96, 2), ("special", 192, 3)])
 def test_grid_families_bit_equal(tmp_path, family, n, ny):
     """text inputs exactly as HelpManager.calc_help_cells hands them over (managers.py:393-428);
-    "deep" = the largest profiles HELP accepts (up to 20 layers / 67 segments: the widest kernel tier)"""
+    "deep" = the largest profiles HELP accepts (up to 20 layers / 67 segments: the widest kernel tier);
+    "special" = the branches no PyHELP grid reaches: geotextile-cushioned geomembranes (FML design cases 5/6,
+    HELP3O.FOR:5177-5285), placement qualities 1 and 5, subsurface inflow into the bottom subprofile (IBAR 4/5
+    and the REAL*8 inflow sums of HELP3O.FOR:2060-2071), IPRE = 1 with initial moisture and snow given, sites
+    at 52-65 deg N and 35 deg S with a growing season across the new year"""
     maker = {"natural3": synth.grid_natural_3layer, "mixed": synth.grid_mixed, "landfill": synth.grid_landfill,
-             "recirc": lambda n, seed: synth.grid_landfill(n, seed=seed, recirc=True), "deep": synth.grid_deep}[family]
+             "recirc": lambda n, seed: synth.grid_landfill(n, seed=seed, recirc=True), "deep": synth.grid_deep,
+             "special": synth.grid_special}[family]
     res = maker(n, seed=21)
     g, ex = res if isinstance(res, tuple) else (res, None)
     nn = 6
@@ -200,3 +205,22 @@ def test_full_size_properties_and_sampled_bits(tmp_path):
     want = oracle.run_help_allcells(cp)
     got = processing.split_by_cell(b.take(sel), {"monthly": m[..., sel], "years": r["years"]})
     assert_bit_equal(got, want)
+
+
+def test_six_subprofiles_and_f73_overflow(tmp_path):
+    """the widest report the reference prints (5 liner systems + a bottom subprofile: the sixth percolation row's
+    Jul-Dec half stays in inches, HELP3O.FOR:6593-6594) and a month over 999.999 mm ('*******' in the reference's
+    text, on which its parser raises; here NaN + HELP_B200_FLAG_OVERFLOW) -- the cases tests/test_outmo2_parser.py
+    pins with the reference's own parser"""
+    import sys
+    sys.path.insert(0, osp.join(osp.dirname(osp.abspath(__file__)), "golden"))
+    import make_outmo2_golden as M
+    cases = M.cases(str(tmp_path))
+    for name in ("six_subprofiles", "overflow", "subin_liner", "geotextile"):
+        cp = {name: cases[name]}
+        got = processing.run_help_allcells(cp)
+        want = oracle.run_help_allcells(cp, ncore=1)
+        assert_bit_equal(got, want)
+    b = inputs.batch_from_cellparams({"overflow": cases["overflow"]})
+    r = processing.run_batch(b)
+    assert r["flags"][0] & N.FLAG_OVERFLOW and np.isnan(r["monthly"][N.HR_PRECIP]).sum() == 1
