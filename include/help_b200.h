@@ -152,6 +152,10 @@ int help_b200_engine_simulate(help_b200_engine* e, void* stream);
 int help_b200_engine_device_ptrs(help_b200_engine* e, void** monthly, void** yearly,
                                  void** raw_monthly, void** flags);
 int help_b200_engine_fetch(help_b200_engine* e, help_b200_result* result);
+
+/* The monthly result in the order of the reference's return value -- one block per cell, out[n_cells][HR_NROWS][n_years][12]
+ * (pyhelp/processing.py:139-146 returns one dict of [n_years][12] arrays per cell) -- transposed on the device.  Host pointer. */
+int help_b200_engine_fetch_monthly_by_cell(help_b200_engine* engine, float* out);
 int help_b200_engine_timings(help_b200_engine* e, float* ms_setup, float* ms_simulate,
                              int32_t* n_launches);
 void help_b200_engine_destroy(help_b200_engine* e);
@@ -199,6 +203,17 @@ int help_b200_nearest_nodes(int64_t n_cells, const double* cell_lat, const doubl
  * first row and number of rows of year y in the table.  Host pointers.                          */
 int help_b200_pack_weather(const double* table, int64_t n_days, int32_t n_nodes, const int32_t* year_day0,
                            const int32_t* year_ndays, int32_t n_years, int32_t decimals, float* out);
+
+/* Fortran formatted READ of fixed-width numeric fields for a whole matrix of records (8f row 1):
+ * the reads READCD (pyhelp/HELP3O.FOR:1100-1129, FORMAT(I10,10F5.2) / (I5,10F6.1)) and READIN (HELP3O.FOR:1221-1225 D11,
+ * :1260-1300 D10) do per cell, done once for all records of a drop-in run_help_allcells(cellparams) call
+ * (pyhelp/processing.py:40-59 receives text).  text[n_records][reclen] bytes (host); field f = columns [col[f], col[f] +
+ * width[f]) read as F<width>.<decimals[f]> (I<width> with decimals 0): blanks ignored, all-blank = 0, an explicit decimal
+ * point overrides the implied decimals, optional E/D exponent.  out[n_fields][n_records] float64 = the correctly rounded
+ * value; flags[n_fields][n_records] = 0, 1 (a valid number that needs more than one exact operation -- more than 15 digits
+ * or a large exponent: convert it on the host) or 2 (not a number).                                                      */
+int help_b200_parse_fields(const uint8_t* text, int64_t n_records, int32_t reclen, const int32_t* col, const int32_t* width,
+                           const int32_t* decimals, int32_t n_fields, double* out, uint8_t* flags);
 
 /* Daily channel: the reference's daily output (IOD = 1: OUTDAY,
  * HELP3O.FOR:5984-6029, parsed by read_daily_help_output, pyhelp/processing.py:150-220) for a

@@ -107,6 +107,10 @@ def lib():
     L.help_b200_nearest_nodes.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     L.help_b200_pack_weather.restype = C.c_int
     L.help_b200_pack_weather.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
+    L.help_b200_parse_fields.restype = C.c_int
+    L.help_b200_parse_fields.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+    L.help_b200_engine_fetch_monthly_by_cell.restype = C.c_int
+    L.help_b200_engine_fetch_monthly_by_cell.argtypes = [C.c_void_p, C.c_void_p]
     if L.help_b200_abi_version() != 1:
         raise EngineError("libhelp_b200.so ABI version mismatch; rebuild")
     _lib = L

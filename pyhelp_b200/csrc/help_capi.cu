@@ -25,6 +25,7 @@
 #include "help_nodes.cuh"
 #include "help_post.cuh"
 #include "help_weather.cuh"
+#include "help_parse.cuh"
 
 using namespace helpb200;
 
@@ -101,8 +102,11 @@ struct help_b200_engine {
   uint64_t *d_key = nullptr, *d_key2 = nullptr; int32_t *d_perm = nullptr, *d_iota = nullptr;
   void* d_cub = nullptr; size_t cub_bytes = 0;
   double* d_daily = nullptr; int32_t* d_daily_row = nullptr; int32_t n_daily = 0; int64_t daily_days = 0;
-  cudaStream_t stream = nullptr;
+  int32_t* d_nnarrow = nullptr;
+  cudaStream_t stream = nullptr, stream2 = nullptr;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  int64_t n_narrow = 0;
   float ms_h2d = 0, ms_setup = 0, ms_sim = 0;
   int n_launches = 0;
   double alg_bytes = 0;
@@ -114,11 +118,14 @@ static void engine_free(help_b200_engine* e) {
   void* ptrs[] = {e->d_years, e->d_pre, e->d_tmp, e->d_rad, e->d_tm, e->d_iu4, e->d_iu7, e->d_iu13, e->d_idfs,
                   e->d_cell_f32, e->d_layer_f32, e->d_cell_i32, e->d_layer_i32, e->d_layer_rc, e->d_img_f32,
                   e->d_img_i32, e->d_img_f64, e->d_img_rec, e->d_monthly, e->d_yearly, e->d_raw, e->d_flags, e->d_topo,
-                  e->d_key, e->d_key2, e->d_perm, e->d_iota, e->d_cub, e->d_daily, e->d_daily_row};
+                  e->d_key, e->d_key2, e->d_perm, e->d_iota, e->d_cub, e->d_daily, e->d_daily_row, e->d_nnarrow};
   cudaDeviceSynchronize();                    // nothing of this engine is in flight when its memory returns to the pool
   for (void* p : ptrs) dev_free(p);
   for (auto& ev : e->ev) if (ev) cudaEventDestroy(ev);
+  if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+  if (e->ev_join) cudaEventDestroy(e->ev_join);
   if (e->stream) cudaStreamDestroy(e->stream);
+  if (e->stream2) cudaStreamDestroy(e->stream2);
   delete e;
 }
 
@@ -198,6 +205,9 @@ extern "C" int help_b200_engine_create(const help_b200_batch* b, int want_monthl
   CUB_(cudaGetDevice(&e->device));
   CUB_(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
   for (auto& ev : e->ev) CUB_(cudaEventCreate(&ev));
+  CUB_(cudaStreamCreateWithFlags(&e->stream2, cudaStreamNonBlocking));
+  CUB_(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
+  CUB_(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
   const int64_t n = b->n_cells;
   const int ny = b->n_years, ml = b->max_layers;
   e->n = n; e->ny = ny;
@@ -230,6 +240,7 @@ extern "C" int help_b200_engine_create(const help_b200_batch* b, int want_monthl
   if (e->want_raw) TRY(dev_alloc(&e->d_raw, (size_t)HELP_B200_RAW_ROWS * ny * 12 * n));
   TRY(dev_alloc(&e->d_yearly, (size_t)HY_NROWS * ny * n));
   TRY(dev_alloc(&e->d_flags, n)); TRY(dev_alloc(&e->d_topo, (size_t)16 * n));
+  TRY(dev_alloc(&e->d_nnarrow, 1));
   TRY(dev_alloc(&e->d_key, n)); TRY(dev_alloc(&e->d_key2, n)); TRY(dev_alloc(&e->d_perm, n)); TRY(dev_alloc(&e->d_iota, n));
   CUB_(cub::DeviceRadixSort::SortPairs(nullptr, e->cub_bytes, e->d_key, e->d_key2, e->d_iota, e->d_perm, (int)n, 0, 64,
                                        e->stream));
@@ -295,10 +306,52 @@ static int pick_shape(int64_t n, int device) {
 }
 
 template <int MAXSEG, int THREADS, int REGS>
-static void launch_sim(const SimArgs& A, int64_t n, cudaStream_t st) {
-  help_sim_kernel<MAXSEG, THREADS, REGS><<<(unsigned)((n + THREADS - 1) / THREADS), THREADS, 0, st>>>(A);
+static void launch_sim(const SimArgs& A, cudaStream_t st) {
+  help_sim_kernel<MAXSEG, THREADS, REGS><<<(unsigned)((A.count + THREADS - 1) / THREADS), THREADS, 0, st>>>(A);
 }
 
+// One launch of image slots [A.first, A.first + A.count) with the instantiation for `maxseg_t` segments;
+// the 16-segment one comes in four register budgets (pick_shape).
+static int launch_tier(const SimArgs& A, int maxseg_t, int device, cudaStream_t st) {
+#ifdef HELP_AB_BIGREG
+  // developer A/B: a launch that cannot fill a quarter of the SMs' thread slots runs with every register a thread can
+  // have (255: no spills) in 64-thread blocks
+  {
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    if ((A.count + sms - 1) / sms <= 256) {
+      switch (maxseg_t) {
+        case 16: launch_sim<16, 64, 255>(A, st); return 0;
+        case 25: launch_sim<25, 64, 255>(A, st); return 0;
+        case 40: launch_sim<40, 64, 255>(A, st); return 0;
+        default: break;
+      }
+    }
+  }
+#endif
+  switch (maxseg_t) {
+    case 16:
+      switch (pick_shape(A.count, device)) {
+        case 0: launch_sim<16, 128, 128>(A, st); break;
+        case 1: launch_sim<16, 128, 96>(A, st); break;
+        case 2: launch_sim<16, 128, 80>(A, st); break;
+        default: launch_sim<16, 128, 64>(A, st); break;
+      }
+      return 0;
+#ifndef HELP_DEV_FAST_BUILD
+    case 25: launch_sim<25, 128, 128>(A, st); return 0;
+    case 40: launch_sim<40, 128, 128>(A, st); return 0;
+    default: launch_sim<67, 128, 128>(A, st); return 0;
+#else
+    default: return fail(HELP_B200_EINVAL, "developer build: MAXSEG 16 only");
+#endif
+  }
+}
+
+// Launch plan (HELP_B200_PLAN overrides: 0 = one launch of the widest instantiation, 1 = narrow tier first,
+// 2 = wide tier first).  The sort puts the narrow tier -- plain profiles of at most 16 segments, i.e. every
+// natural-soil cell -- in front; when a batch also holds liner profiles the two tiers are launched separately,
+// each with its own instantiation, on two streams so that the second fills the SMs as the first drains.
 extern "C" int help_b200_engine_simulate(help_b200_engine* e, void* stream) {
   if (!e) return fail(HELP_B200_EINVAL, "engine is NULL");
   CU(cudaSetDevice(e->device));
@@ -310,38 +363,54 @@ extern "C" int help_b200_engine_simulate(help_b200_engine* e, void* stream) {
   if (n > 0) {
     const unsigned gs = (unsigned)((n + 63) / 64);
     const int32_t* perm = nullptr;
+    int64_t n_narrow = 0;
     if (e->sort) {
-      help_setup_kernel<<<gs, 64, 0, st>>>(e->B, img, nullptr, nullptr, nullptr, e->d_key);
+      CU(cudaMemsetAsync(e->d_nnarrow, 0, sizeof(int32_t), st));
+      help_setup_kernel<<<gs, 64, 0, st>>>(e->B, img, nullptr, nullptr, nullptr, e->d_key, e->d_nnarrow);
       CU(cub::DeviceRadixSort::SortPairs(e->d_cub, e->cub_bytes, e->d_key, e->d_key2, e->d_iota, e->d_perm, (int)n, 0, 64, st));
       perm = e->d_perm;
       e->n_launches += 2;   // + the radix-sort passes, which are library kernels and not counted
+      int32_t h = 0;
+      CU(cudaMemcpyAsync(&h, e->d_nnarrow, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+      CU(cudaStreamSynchronize(st));
+      n_narrow = h;
     }
-    help_setup_kernel<<<gs, 64, 0, st>>>(e->B, img, perm, e->d_flags, e->d_topo, nullptr);
+    e->n_narrow = n_narrow;
+    help_setup_kernel<<<gs, 64, 0, st>>>(e->B, img, perm, e->d_flags, e->d_topo, nullptr, nullptr);
     e->n_launches += 1;
     CU(cudaEventRecord(e->ev[1], st));
     SimArgs A;
     A.img = img; A.pre = e->d_pre; A.tmp = e->d_tmp; A.rad = e->d_rad; A.years = e->d_years;
-    A.n_years = e->ny; A.n_cells = n; A.perm = perm;
+    A.n_years = e->ny; A.n_cells = n; A.first = 0; A.count = n; A.perm = perm;
     A.monthly = e->d_monthly; A.yearly = e->d_yearly; A.raw = e->d_raw; A.flags = e->d_flags;
     A.daily = e->d_daily; A.daily_row = e->d_daily_row; A.daily_days = e->daily_days;
-    switch (e->maxseg_t) {
-      case 16:
-        switch (pick_shape(n, e->device)) {
-          case 0: launch_sim<16, 128, 128>(A, n, st); break;
-          case 1: launch_sim<16, 128, 96>(A, n, st); break;
-          case 2: launch_sim<16, 128, 80>(A, n, st); break;
-          default: launch_sim<16, 128, 64>(A, n, st); break;
-        }
-        break;
-#ifndef HELP_DEV_FAST_BUILD
-      case 25: launch_sim<25, 128, 128>(A, n, st); break;
-      case 40: launch_sim<40, 128, 128>(A, n, st); break;
-      default: launch_sim<67, 128, 128>(A, n, st); break;
-#else
-      default: return fail(HELP_B200_EINVAL, "developer build: MAXSEG 16 only");
-#endif
+    int plan = 1;
+    if (const char* f = getenv("HELP_B200_PLAN")) plan = atoi(f);
+    int rc = 0;
+    if (n_narrow == n && e->sort) {
+      rc = launch_tier(A, 16, e->device, st);                       // every cell is narrow, whatever max_layers says
+      e->n_launches += 1;
+    } else if (plan == 0 || n_narrow == 0 || !e->sort) {
+      rc = launch_tier(A, e->maxseg_t, e->device, st);
+      e->n_launches += 1;
+    } else {
+      SimArgs N1 = A, W = A;
+      N1.first = 0; N1.count = n_narrow;
+      W.first = n_narrow; W.count = n - n_narrow;
+      CU(cudaEventRecord(e->ev_fork, st));
+      CU(cudaStreamWaitEvent(e->stream2, e->ev_fork, 0));
+      if (plan == 2) {
+        rc = launch_tier(W, e->maxseg_t, e->device, st);
+        if (!rc) rc = launch_tier(N1, 16, e->device, e->stream2);
+      } else {
+        rc = launch_tier(N1, 16, e->device, st);
+        if (!rc) rc = launch_tier(W, e->maxseg_t, e->device, e->stream2);
+      }
+      CU(cudaEventRecord(e->ev_join, e->stream2));
+      CU(cudaStreamWaitEvent(st, e->ev_join, 0));
+      e->n_launches += 2;
     }
-    e->n_launches += 1;
+    if (rc) return rc;
   } else {
     CU(cudaEventRecord(e->ev[1], st));
   }
@@ -391,6 +460,26 @@ extern "C" int help_b200_engine_fetch(help_b200_engine* e, help_b200_result* r) 
   CU(cudaStreamSynchronize(st));
   CU(cudaEventElapsedTime(&r->ms_d2h, e->ev[0], e->ev[1]));
   r->ms_h2d = e->ms_h2d; r->ms_setup = e->ms_setup; r->ms_simulate = e->ms_sim; r->n_launches = e->n_launches;
+  return 0;
+}
+
+extern "C" int help_b200_engine_fetch_monthly_by_cell(help_b200_engine* e, float* out) {
+  if (!e || !out) return fail(HELP_B200_EINVAL, "engine or out is NULL");
+  if (!e->d_monthly) return fail(HELP_B200_EINVAL, "monthly was not requested at engine_create");
+  CU(cudaSetDevice(e->device));
+  const int64_t n = e->n, rows = (int64_t)HR_NROWS * e->ny * 12;
+  if (n == 0) return 0;
+  float* d_t = nullptr;
+  int rc = dev_alloc(&d_t, (size_t)rows * n);
+  if (rc) return rc;
+  cudaStream_t st = e->stream;
+  const dim3 grid((unsigned)((n + 31) / 32), (unsigned)((rows + 31) / 32));
+  transpose_to_cell_major_kernel<<<grid, dim3(32, 8), 0, st>>>(e->d_monthly, rows, n, d_t);
+  cudaError_t ce = cudaGetLastError();
+  if (ce == cudaSuccess) ce = cudaMemcpyAsync(out, d_t, sizeof(float) * rows * n, cudaMemcpyDeviceToHost, st);
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+  dev_free(d_t);
+  if (ce != cudaSuccess) return fail(HELP_B200_ECUDA, "fetch_monthly_by_cell", ce);
   return 0;
 }
 
@@ -594,6 +683,36 @@ extern "C" int help_b200_pack_weather(const double* table, int64_t n_days, int32
   }
   if (ce == cudaSuccess) ce = cudaMemcpy(out, d_out, sizeof(float) * n_out, cudaMemcpyDeviceToHost);
   if (ce != cudaSuccess) return done(fail(HELP_B200_ECUDA, "pack_weather", ce));
+  return done(0);
+}
+
+extern "C" int help_b200_parse_fields(const uint8_t* text, int64_t n_records, int32_t reclen, const int32_t* col,
+                                      const int32_t* width, const int32_t* decimals, int32_t n_fields, double* out, uint8_t* flags) {
+  if (!text || !col || !width || !decimals || !out || !flags || n_records < 0 || reclen < 1 || n_fields < 1 || n_fields > 64)
+    return fail(HELP_B200_EINVAL, "parse_fields: bad argument");
+  for (int f = 0; f < n_fields; ++f)
+    if (col[f] < 0 || width[f] < 1 || col[f] >= reclen || decimals[f] < 0 || decimals[f] > 22)
+      return fail(HELP_B200_EINVAL, "parse_fields: a field lies outside the record");
+  if (help_b200_device_count() < 1) return fail(HELP_B200_ENODEV, "no CUDA device (this engine has no CPU path)");
+  if (n_records == 0) return 0;
+  uint8_t *d_text = nullptr, *d_flag = nullptr; int32_t* d_spec = nullptr; double* d_out = nullptr;
+  int rc = 0;
+  auto done = [&](int code) { cudaDeviceSynchronize(); dev_free(d_text); dev_free(d_flag); dev_free(d_spec); dev_free(d_out); return code; };
+  const size_t nt = (size_t)n_records * reclen, nv = (size_t)n_records * n_fields;
+  if ((rc = dev_alloc(&d_text, nt)) || (rc = dev_alloc(&d_flag, nv)) || (rc = dev_alloc(&d_spec, (size_t)3 * n_fields)) || (rc = dev_alloc(&d_out, nv)))
+    return done(rc);
+  cudaError_t ce = cudaMemcpy(d_text, text, nt, cudaMemcpyHostToDevice);
+  if (ce == cudaSuccess) ce = cudaMemcpy(d_spec, col, sizeof(int32_t) * n_fields, cudaMemcpyHostToDevice);
+  if (ce == cudaSuccess) ce = cudaMemcpy(d_spec + n_fields, width, sizeof(int32_t) * n_fields, cudaMemcpyHostToDevice);
+  if (ce == cudaSuccess) ce = cudaMemcpy(d_spec + 2 * n_fields, decimals, sizeof(int32_t) * n_fields, cudaMemcpyHostToDevice);
+  if (ce == cudaSuccess) {
+    parse_fields_kernel<<<(unsigned)((nv + 255) / 256), 256>>>(d_text, n_records, reclen, d_spec, d_spec + n_fields, d_spec + 2 * n_fields,
+                                                              n_fields, d_out, d_flag);
+    ce = cudaGetLastError();
+  }
+  if (ce == cudaSuccess) ce = cudaMemcpy(out, d_out, sizeof(double) * nv, cudaMemcpyDeviceToHost);
+  if (ce == cudaSuccess) ce = cudaMemcpy(flags, d_flag, nv, cudaMemcpyDeviceToHost);
+  if (ce != cudaSuccess) return done(fail(HELP_B200_ECUDA, "parse_fields", ce));
   return done(0);
 }
 

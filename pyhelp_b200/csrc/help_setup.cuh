@@ -452,7 +452,7 @@ __device__ inline float heat_units(int M, int K, float A1, float A2, float A3) {
 
 __global__ void __launch_bounds__(64)
 help_setup_kernel(BatchDev B, Image img, const int32_t* __restrict__ perm, uint32_t* __restrict__ flags,
-                  int32_t* __restrict__ topo, uint64_t* __restrict__ sortkey) {
+                  int32_t* __restrict__ topo, uint64_t* __restrict__ sortkey, int32_t* __restrict__ n_narrow) {
   helpmath::hm_load_tables();
   const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // position in the (sorted) image
   if (slot >= B.n_cells) return;
@@ -782,7 +782,13 @@ help_setup_kernel(BatchDev B, Image img, const int32_t* __restrict__ perm, uint3
     }
     if (cost > 0xFFFFull) cost = 0xFFFFull;
     const uint64_t soil = ((uint64_t)(uint32_t)__float_as_int(S.RCUL[1]) >> 21) & 0x3FFull;
-    sortkey[slot] = ((cls & 0xFFFFull) << 48) | (cost << 32) | (((uint64_t)node_t & 0x3FFFFFull) << 10) | soil;
+    // Most significant bit: the launch tier.  0 = one plain subprofile (no liner, drain layer or inflow) of at most 16
+    // segments -- every natural-soil PyHELP cell: these go to the narrow kernel instantiation (16-segment state, the
+    // register budget that fills one wave); 1 = everything else (help_capi.cu launch plan).
+    const bool narrow = (nprof == 1) && (img.PI(Q_SUBIN, 1, slot) & 2) && S.NSEG <= 16 && !(flag & kFlagRecirc);
+    if (narrow && n_narrow) atomicAdd(n_narrow, 1);
+    sortkey[slot] = ((uint64_t)(narrow ? 0 : 1) << 63) | ((cls & 0x7FFFull) << 48) | (cost << 32) |
+                    (((uint64_t)node_t & 0x3FFFFFull) << 10) | soil;
   }
 }
 

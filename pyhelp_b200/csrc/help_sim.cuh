@@ -50,7 +50,8 @@ struct SimArgs {
   const float* rad;       // langley/day
   const int32_t* years;   // [n_years]
   int n_years;
-  int64_t n_cells;
+  int64_t n_cells;        // cells of the batch (stride of the result arrays)
+  int64_t first, count;   // image slots [first, first + count) are simulated by this launch
   const int32_t* perm;    // image slot -> caller's cell index (NULL = identity)
   float* monthly;         // [7][ny][12][n] or NULL
   float* yearly;          // [5][ny][n] or NULL
@@ -597,8 +598,8 @@ __global__ void __launch_bounds__(THREADS) __maxnreg__(REGS) help_sim_kernel(Sim
   // be simulated, reads the last cell's constants (valid addresses) and sits out every day
   // (`live == false`); it only keeps the barrier count.
   const int64_t s_raw = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  bool live = s_raw < A.n_cells;
-  const int64_t s = live ? s_raw : A.n_cells - 1;
+  bool live = s_raw < A.count;
+  const int64_t s = A.first + (live ? s_raw : A.count - 1);
   const Image& img = A.img;
   const int64_t n = A.n_cells;
   const int64_t cell = A.perm ? A.perm[s] : s;

@@ -78,6 +78,37 @@ def _records(lines, reclen=80) -> np.ndarray:
     return np.frombuffer(a.astype(f"S{reclen}").tobytes(), dtype=np.uint8).reshape(-1, reclen)
 
 
+def parse_matrix(rec: np.ndarray, specs, where: str = "host") -> np.ndarray:
+    """Formatted READ of the fields ``specs`` = [(first column, width, implied decimals), ...] from every record of the
+    (n, reclen) uint8 matrix ``rec``: float64 [n_fields][n].  ``where="device"`` does it in one kernel
+    (``help_b200_parse_fields``, csrc/help_parse.cuh; same values: tests/test_gpu_pack.py); fields the kernel marks as
+    needing more than one exact operation are converted here, fields that are not numbers raise ValueError like
+    numpy's conversion does on the host path."""
+    n = rec.shape[0]
+    out = np.zeros((len(specs), n), dtype=np.float64)
+    if n == 0:
+        return out
+    if where == "host":
+        for k, (a, w, d) in enumerate(specs):
+            out[k] = _to_real(_field(rec, a, w), d, np.float64)
+        return out
+    if where != "device":
+        raise ValueError("where must be 'host' or 'device'")
+    rec = np.ascontiguousarray(rec)
+    col = np.array([s[0] for s in specs], dtype=np.int32)
+    wid = np.array([s[1] for s in specs], dtype=np.int32)
+    dec = np.array([s[2] for s in specs], dtype=np.int32)
+    flags = np.zeros((len(specs), n), dtype=np.uint8)
+    N.require_device()
+    N.check(N.lib().help_b200_parse_fields(N.ptr(rec), n, rec.shape[1], N.ptr(col), N.ptr(wid), N.ptr(dec), len(specs),
+                                           N.ptr(out), N.ptr(flags)), "parse_fields")
+    if flags.any():
+        for k, r in zip(*np.nonzero(flags)):
+            a, w, d = specs[k]
+            out[k, r] = _to_real(_field(rec[r:r + 1], a, w), d, np.float64)[0]      # raises ValueError for a non-number
+    return out
+
+
 # ----------------------------------------------------------------------------
 # Weather files (D4 / D7 / D13)
 # ----------------------------------------------------------------------------
@@ -91,8 +122,9 @@ class WeatherFile:
     idfs: tuple = (1, 1)   # (ULAT >= 0, ULAT < 0), D13 only
 
 
-def read_weather_file(path: str, kind: str) -> WeatherFile:
-    """READIN header read (F:1215-1218) + READCD year blocks (F:1100-1129)."""
+def _load_weather_records(path: str):
+    """(header records (4, 80), data records (37 * nblocks, 80), nblocks) of one D4/D7/D13 file as uint8 matrices
+    (records cut or blank-padded to 80 columns, CR dropped)."""
     with open(path, "rb") as f:
         lines = f.read().split(b"\n")
     if lines and lines[-1] == b"":
@@ -102,31 +134,56 @@ def read_weather_file(path: str, kind: str) -> WeatherFile:
     nblocks = (len(lines) - 4) // 37
     if nblocks < 1:
         raise ValueError(f"{path}: no complete year of data")
-    # one byte matrix for the whole file (records cut or blank-padded to 80 columns, CR dropped)
     allrec = _records(np.array(lines[:4 + 37 * nblocks], dtype="S80"))
     allrec[allrec == 13] = 32
     allrec[allrec > 127] = 63
-    hdr, rec = allrec[:4], allrec[4:]
-    units = int(_to_int(_field(hdr[1:2], 0, 2))[0])
-    h12 = np.ascontiguousarray(hdr[3, :72]).reshape(12, 6)
-    header12 = _to_real(np.char.strip(h12.view("S6").reshape(-1)), 2, F32)
+    return allrec[:4], allrec[4:], nblocks
+
+
+def read_weather_files(paths, kind: str, where: str = "host") -> list:
+    """READIN header read (F:1215-1218) + READCD year blocks (F:1100-1129) of several files of one kind: the records
+    of all files are converted in one :func:`parse_matrix` call."""
+    loads = [_load_weather_records(os.fspath(p)) for p in paths]
+    if not loads:
+        return []
+    hdr = np.stack([h for h, _, _ in loads])                               # (nf, 4, 80)
+    units = _to_int(_field(np.ascontiguousarray(hdr[:, 1]), 0, 2))
+    h12 = np.ascontiguousarray(hdr[:, 3, :72]).reshape(-1, 6)
+    header12 = _to_real(np.char.strip(h12.view("S6").reshape(-1)), 2, F32).reshape(-1, 12)
+    rec = np.concatenate([r for _, r, _ in loads]) if len(loads) > 1 else loads[0][1]
     if kind == "D4":      # FORMAT(I10,10F5.2)
-        ycol, y_w, v0, v_w, d = 0, 10, 10, 5, 2
+        y_w, v0, v_w = 10, 10, 5
     else:                 # FORMAT(I5,10F6.1) / (I5,10F6.0)
-        ycol, y_w, v0, v_w = 0, 5, 5, 6
-        d = 1 if (kind == "D7" or units == 1) else 0
-    yrs = _to_int(_field(rec, ycol, y_w)).reshape(nblocks, 37)[:, -1]
-    vals = np.ascontiguousarray(rec[:, v0:v0 + 10 * v_w]).reshape(-1, v_w)            # [record x 10 fields][v_w]
-    vals = _to_real(np.char.strip(vals.view(f"S{v_w}").reshape(-1)), d, F32)
-    data = vals.reshape(nblocks, 370)[:, :366].astype(F32)
-    wf = WeatherFile(kind, units, yrs.astype(np.int32), np.ascontiguousarray(data), header12)
+        y_w, v0, v_w = 5, 5, 6
+    nrec = np.array([r.shape[0] for _, r, _ in loads])
+    file_of = np.repeat(np.arange(len(loads)), nrec)
+    # the implied decimals depend on the file's units for D13 (F:1127-1128); READIN's pre-scan of D13 always reads F6.1
+    # (formats 5400/5410, F:1364-1365): both variants are read, they differ only for fields without a decimal point
+    d_main = {"D4": 2, "D7": 1}.get(kind)
+    specs = [(0, y_w, 0)] + [(v0 + k * v_w, v_w, d_main if d_main is not None else 1) for k in range(10)]
     if kind == "D13":
-        # READIN's pre-scan reads the same fields with F6.1 whatever the units (formats 5400/5410,
-        # F:1364-1365) while READCD reads SI files with F6.0 (F:1128): fields written without a
-        # decimal point are ten times smaller in the pre-scan
-        pre = data if d == 1 else _to_real(np.char.strip(np.ascontiguousarray(rec[:, v0:v0 + 10 * v_w]).reshape(-1, v_w).view(f"S{v_w}").reshape(-1)), 1, F32).reshape(nblocks, 370)[:, :366]
-        wf.idfs = idfs_prescan(pre, units)
-    return wf
+        specs += [(v0 + k * v_w, v_w, 0) for k in range(10)]
+    vals = parse_matrix(rec, specs, where)
+    out, pos = [], 0
+    for i, (_, r, nblocks) in enumerate(loads):
+        sl = slice(pos, pos + r.shape[0])
+        pos += r.shape[0]
+        yrs = vals[0, sl].astype(np.int64).astype(np.int32).reshape(nblocks, 37)[:, -1]
+        v1 = vals[1:11, sl].T.reshape(nblocks, 370)[:, :366].astype(F32)              # (.., d = 2 / 1)
+        if kind == "D13" and int(units[i]) != 1:
+            data = vals[11:21, sl].T.reshape(nblocks, 370)[:, :366].astype(F32)        # READCD: F6.0 for SI radiation
+        else:
+            data = v1
+        wf = WeatherFile(kind, int(units[i]), yrs, np.ascontiguousarray(data), header12[i].astype(F32))
+        if kind == "D13":
+            wf.idfs = idfs_prescan(v1, int(units[i]))
+        out.append(wf)
+    return out
+
+
+def read_weather_file(path: str, kind: str) -> WeatherFile:
+    """One file (host conversion)."""
+    return read_weather_files([path], kind, "host")[0]
 
 
 def idfs_prescan(rad: np.ndarray, iu13: int) -> tuple:
@@ -154,71 +211,86 @@ def idfs_prescan(rad: np.ndarray, iu13: int) -> tuple:
 # ----------------------------------------------------------------------------
 # D11 / D10 records
 # ----------------------------------------------------------------------------
-def parse_d11(rec3: np.ndarray, cell_f32: np.ndarray, cell_i32: np.ndarray, idx: np.ndarray):
+D11_SPECS = [(0, 10, 2), (10, 4, 0), (14, 4, 0), (18, 7, 0), (25, 8, 0), (33, 5, 0), (38, 5, 0), (43, 5, 0), (48, 5, 0), (53, 5, 0)]
+D10_HEAD_SPECS = [(0, 2, 0), (2, 2, 0), (4, 10, 0), (24, 6, 0), (30, 2, 0)]
+D10_A_SPECS = [(0, 2, 0), (2, 7, 0), (9, 4, 0), (13, 6, 0), (19, 6, 0), (25, 6, 0), (31, 6, 0), (37, 16, 0)]
+D10_B_SPECS = [(0, 7, 0), (7, 6, 0), (13, 6, 0), (19, 3, 0), (22, 13, 0), (35, 7, 0), (42, 7, 0), (49, 2, 0), (51, 14, 6)]
+
+
+def _i32(v):
+    return v.astype(np.int64).astype(np.int32)
+
+
+def parse_d11(rec3: np.ndarray, cell_f32: np.ndarray, cell_i32: np.ndarray, idx: np.ndarray, where: str = "host"):
     """rec3: (m, 3, 80) uint8.  F:1221-1225: (I2) ; (F10.2,I4,I4,F7.0,F8.0,5F5.0)."""
-    r1, r3 = rec3[:, 0], rec3[:, 2]
-    cell_i32[N.HB_IU11, idx] = _to_int(_field(r1, 0, 2))
-    cell_f32[N.HB_ULAT, idx] = _to_real(_field(r3, 0, 10), 2, F32)
-    cell_i32[N.HB_IPL, idx] = _to_int(_field(r3, 10, 4))
-    cell_i32[N.HB_IHV, idx] = _to_int(_field(r3, 14, 4))
-    cell_f32[N.HB_ULAI, idx] = _to_real(_field(r3, 18, 7), 0, F32)
-    cell_f32[N.HB_EDEPTH, idx] = _to_real(_field(r3, 25, 8), 0, F32)
-    cell_f32[N.HB_WIND, idx] = _to_real(_field(r3, 33, 5), 0, F32)
+    cell_i32[N.HB_IU11, idx] = _i32(parse_matrix(np.ascontiguousarray(rec3[:, 0]), [(0, 2, 0)], where)[0])
+    v = parse_matrix(np.ascontiguousarray(rec3[:, 2]), D11_SPECS, where)
+    cell_f32[N.HB_ULAT, idx] = v[0].astype(F32)
+    cell_i32[N.HB_IPL, idx] = _i32(v[1])
+    cell_i32[N.HB_IHV, idx] = _i32(v[2])
+    cell_f32[N.HB_ULAI, idx] = v[3].astype(F32)
+    cell_f32[N.HB_EDEPTH, idx] = v[4].astype(F32)
+    cell_f32[N.HB_WIND, idx] = v[5].astype(F32)
     for q in range(4):
-        cell_f32[N.HB_HUM1 + q, idx] = _to_real(_field(r3, 38 + 5 * q, 5), 0, F32)
+        cell_f32[N.HB_HUM1 + q, idx] = v[6 + q].astype(F32)
 
 
-def parse_d10(rec: np.ndarray, cell_f32, cell_i32, layer_f32, layer_i32, layer_rc, idx: np.ndarray):
+def parse_d10(rec: np.ndarray, cell_f32, cell_i32, layer_f32, layer_i32, layer_rc, idx: np.ndarray, where: str = "host"):
     """rec: (m, nrec, 80) uint8 with a common record count.  F:1260-1300."""
     m, nrec = rec.shape[0], rec.shape[1]
-    r2 = rec[:, 1]                       # FORMAT(I2,I2,2F10.0,F6.0,I2)
-    cell_i32[N.HB_IU10, idx] = _to_int(_field(r2, 0, 2))
-    cell_i32[N.HB_IPRE, idx] = _to_int(_field(r2, 2, 2))
-    cell_f32[N.HB_OSNO, idx] = _to_real(_field(r2, 4, 10), 0, F32)
-    cell_f32[N.HB_FRUNOF, idx] = _to_real(_field(r2, 24, 6), 0, F32)
-    irun = _to_int(_field(r2, 30, 2))
-    r3 = rec[:, 2]
+    h = parse_matrix(np.ascontiguousarray(rec[:, 1]), D10_HEAD_SPECS, where)      # FORMAT(I2,I2,2F10.0,F6.0,I2)
+    cell_i32[N.HB_IU10, idx] = _i32(h[0])
+    cell_i32[N.HB_IPRE, idx] = _i32(h[1])
+    cell_f32[N.HB_OSNO, idx] = h[2].astype(F32)
+    cell_f32[N.HB_FRUNOF, idx] = h[3].astype(F32)
+    irun = _i32(h[4])
+    r3 = np.ascontiguousarray(rec[:, 2])
     cn = np.zeros(m, dtype=F32)
     nxt = np.full(m, 2, dtype=np.int64)  # record index of the first layer record
     for code, col in ((1, 0), (2, 21), (3, 20)):   # F:1268-1281: where CN2 sits for IRUN = 1 / 2 / 3
         sel = irun == code
         if sel.any():
-            cn[sel] = _to_real(_field(r3[sel], col, 7), 0, F32)
+            cn[sel] = parse_matrix(r3[sel], [(col, 7, 0)], where)[0].astype(F32)
             nxt[sel] = 3
     cell_f32[N.HB_CN2, idx] = cn
     # layers: two records each; a trailing unpaired first record still counts (F:1284-1297)
     nlay = np.minimum((nrec - nxt + 1) // 2, 20).astype(np.int32)
     nlay = np.maximum(nlay, 0)
     cell_i32[N.HB_NLAY, idx] = nlay
-    for j in range(int(nlay.max()) if m else 0):
-        has1 = nlay > j
-        rows = np.nonzero(has1)[0]
-        if rows.size == 0:
-            break
-        ra = rec[rows, nxt[rows] + 2 * j]           # FORMAT(I2,F7.0,I4,4F6.0,F16.0)
-        tgt = idx[rows]
-        layer_i32[N.HL_TYPE, j, tgt] = _to_int(_field(ra, 0, 2))
-        layer_f32[N.HL_THICK, j, tgt] = _to_real(_field(ra, 2, 7), 0, F32)
-        layer_i32[N.HL_ISOIL, j, tgt] = _to_int(_field(ra, 9, 4))
-        layer_f32[N.HL_PORO, j, tgt] = _to_real(_field(ra, 13, 6), 0, F32)
-        layer_f32[N.HL_FC, j, tgt] = _to_real(_field(ra, 19, 6), 0, F32)
-        layer_f32[N.HL_WP, j, tgt] = _to_real(_field(ra, 25, 6), 0, F32)
-        layer_f32[N.HL_SW, j, tgt] = _to_real(_field(ra, 31, 6), 0, F32)
-        layer_rc[j, tgt] = _to_real(_field(ra, 37, 16), 0, np.float64)
-        has2 = (nxt[rows] + 2 * j + 1) < nrec
-        rows2 = rows[has2]
-        if rows2.size:
-            rb = rec[rows2, nxt[rows2] + 2 * j + 1]  # FORMAT(F7.0,2F6.0,I3,F13.0,2F7.0,I2,G14.6)
-            tg2 = idx[rows2]
-            layer_f32[N.HL_XLENG, j, tg2] = _to_real(_field(rb, 0, 7), 0, F32)
-            layer_f32[N.HL_SLOPE, j, tg2] = _to_real(_field(rb, 7, 6), 0, F32)
-            layer_f32[N.HL_RECIR, j, tg2] = _to_real(_field(rb, 13, 6), 0, F32)
-            layer_i32[N.HL_LAYR, j, tg2] = _to_int(_field(rb, 19, 3))
-            layer_f32[N.HL_SUBIN, j, tg2] = _to_real(_field(rb, 22, 13), 0, F32)
-            layer_f32[N.HL_PHOLE, j, tg2] = _to_real(_field(rb, 35, 7), 0, F32)
-            layer_f32[N.HL_DEFEC, j, tg2] = _to_real(_field(rb, 42, 7), 0, F32)
-            layer_i32[N.HL_IPQ, j, tg2] = _to_int(_field(rb, 49, 2))
-            layer_f32[N.HL_TRANS, j, tg2] = _to_real(_field(rb, 51, 14), 6, F32)
+    L = int(nlay.max()) if m else 0
+    if L == 0:
+        return
+    # every first ("A") and second ("B") layer record of the group in two matrices: two conversions for all layers
+    rows_a, lay_a, rows_b, lay_b = [], [], [], []
+    for j in range(L):
+        rows = np.nonzero(nlay > j)[0]
+        rows_a.append(rows); lay_a.append(np.full(rows.size, j))
+        rows2 = rows[(nxt[rows] + 2 * j + 1) < nrec]
+        rows_b.append(rows2); lay_b.append(np.full(rows2.size, j))
+    rows_a, lay_a = np.concatenate(rows_a), np.concatenate(lay_a)
+    rows_b, lay_b = np.concatenate(rows_b), np.concatenate(lay_b)
+    va = parse_matrix(rec[rows_a, nxt[rows_a] + 2 * lay_a], D10_A_SPECS, where)        # FORMAT(I2,F7.0,I4,4F6.0,F16.0)
+    tgt = idx[rows_a]
+    layer_i32[N.HL_TYPE, lay_a, tgt] = _i32(va[0])
+    layer_f32[N.HL_THICK, lay_a, tgt] = va[1].astype(F32)
+    layer_i32[N.HL_ISOIL, lay_a, tgt] = _i32(va[2])
+    layer_f32[N.HL_PORO, lay_a, tgt] = va[3].astype(F32)
+    layer_f32[N.HL_FC, lay_a, tgt] = va[4].astype(F32)
+    layer_f32[N.HL_WP, lay_a, tgt] = va[5].astype(F32)
+    layer_f32[N.HL_SW, lay_a, tgt] = va[6].astype(F32)
+    layer_rc[lay_a, tgt] = va[7]
+    if rows_b.size:
+        vb = parse_matrix(rec[rows_b, nxt[rows_b] + 2 * lay_b + 1], D10_B_SPECS, where)  # FORMAT(F7.0,2F6.0,I3,F13.0,2F7.0,I2,G14.6)
+        tg2 = idx[rows_b]
+        layer_f32[N.HL_XLENG, lay_b, tg2] = vb[0].astype(F32)
+        layer_f32[N.HL_SLOPE, lay_b, tg2] = vb[1].astype(F32)
+        layer_f32[N.HL_RECIR, lay_b, tg2] = vb[2].astype(F32)
+        layer_i32[N.HL_LAYR, lay_b, tg2] = _i32(vb[3])
+        layer_f32[N.HL_SUBIN, lay_b, tg2] = vb[4].astype(F32)
+        layer_f32[N.HL_PHOLE, lay_b, tg2] = vb[5].astype(F32)
+        layer_f32[N.HL_DEFEC, lay_b, tg2] = vb[6].astype(F32)
+        layer_i32[N.HL_IPQ, lay_b, tg2] = _i32(vb[7])
+        layer_f32[N.HL_TRANS, lay_b, tg2] = vb[8].astype(F32)
 
 
 # ----------------------------------------------------------------------------
@@ -296,33 +368,30 @@ def pack_weather(files_p, files_t, files_r, n_years: int):
             np.ascontiguousarray(np.array([w.idfs for w in files_r], dtype=np.int32).reshape(-1, 2)))
 
 
-def batch_from_cellparams(cellparams: dict) -> CellBatch:
+def batch_from_cellparams(cellparams: dict, parse: str = "host") -> CellBatch:
     """``cellparams`` exactly as ``HelpManager.calc_help_cells`` builds it
     (reference managers.py:422-428): name -> (d4, d7, d13, d11 S80[3], d10 S80[n],
-    fpath_out, iod, iom, ioa, ios, simu_nyear, tfsoil_F)."""
+    fpath_out, iod, iom, ioa, ios, simu_nyear, tfsoil_F).  ``parse``: where the formatted reads of the
+    records and weather files run -- ``"host"`` (numpy) or ``"device"`` (:func:`parse_matrix`)."""
     names = list(cellparams.keys())
     n = len(names)
     nyears = {int(p[10]) for p in cellparams.values()}
     if len(nyears) > 1:
         raise ValueError("all cells of one batch must simulate the same number of years")
     n_years = nyears.pop() if nyears else 1
-    cache: dict = {}
+    tables = ({}, {}, {})                                    # path -> node index, per kind, in order of first use
 
-    def node(path, kind, table, order):
+    def node(path, kind, table):
         key = os.fspath(path)
         if isinstance(key, bytes):
             key = key.decode()
         key = key.strip()
         if key not in table:
-            if key not in cache:
-                if not os.path.exists(key):
-                    raise FileNotFoundError(f"{kind} weather file not found: {key}")
-                cache[key] = read_weather_file(key, kind)
-            table[key] = len(order)
-            order.append(cache[key])
+            if not os.path.exists(key):
+                raise FileNotFoundError(f"{kind} weather file not found: {key}")
+            table[key] = len(table)
         return table[key]
 
-    tp, tt, tr, fp, ft, fr = {}, {}, {}, [], [], []
     cell_f32 = np.zeros((N.HB_NCELL_F32, n), dtype=F32)
     cell_i32 = np.zeros((N.HB_NCELL_I32, n), dtype=np.int32)
     # Records are gathered per cell and converted to byte matrices in a few large calls (one per
@@ -340,9 +409,9 @@ def batch_from_cellparams(cellparams: dict) -> CellBatch:
     last = [None, None, None, 0, 0, 0]                       # consecutive cells usually share their weather files
     for i, name in enumerate(names):
         p = cellparams[name]
-        for k, (kind, table, order) in enumerate((("D4", tp, fp), ("D7", tt, ft), ("D13", tr, fr))):
+        for k, kind in enumerate(("D4", "D7", "D13")):
             if p[k] is not last[k]:
-                last[k], last[3 + k] = p[k], node(p[k], kind, table, order)
+                last[k], last[3 + k] = p[k], node(p[k], kind, tables[k])
             node_ids[k, i] = last[3 + k]
         r11 = as_s80(p[3])
         if r11.shape[0] < 3:
@@ -353,9 +422,12 @@ def batch_from_cellparams(cellparams: dict) -> CellBatch:
         g10[0].append(i)
         g10[1].append(r10)
         tfsoil[i] = p[11]
+    if n == 0:
+        raise ValueError("cellparams is empty")
+    fp, ft, fr = (read_weather_files(list(t.keys()), kind, parse) for t, kind in zip(tables, ("D4", "D7", "D13")))
     cell_i32[N.HB_NODE_P], cell_i32[N.HB_NODE_T], cell_i32[N.HB_NODE_R] = node_ids
     cell_f32[N.HB_TFSOIL] = tfsoil.astype(F32)
-    d11_rec = _records(np.concatenate(d11_list)).reshape(n, 3, 80) if n else np.zeros((0, 3, 80), dtype=np.uint8)
+    d11_rec = _records(np.concatenate(d11_list)).reshape(n, 3, 80)
     d10_groups = {nrec: (idx, _records(np.concatenate(recs)).reshape(len(idx), nrec, 80))
                   for nrec, (idx, recs) in d10_lists.items()}
     max_layers = 1
@@ -364,13 +436,11 @@ def batch_from_cellparams(cellparams: dict) -> CellBatch:
     layer_f32 = np.zeros((N.HL_NLAYER_F32, max_layers, n), dtype=F32)
     layer_i32 = np.zeros((N.HL_NLAYER_I32, max_layers, n), dtype=np.int32)
     layer_rc = np.zeros((max_layers, n), dtype=np.float64)
-    parse_d11(d11_rec, cell_f32, cell_i32, np.arange(n))
+    parse_d11(d11_rec, cell_f32, cell_i32, np.arange(n), parse)
     for nrec, (idx, recs) in d10_groups.items():
         if nrec < 3:
             raise ValueError("a D10 input needs at least 3 records")
-        parse_d10(recs, cell_f32, cell_i32, layer_f32, layer_i32, layer_rc, np.asarray(idx))
-    if n == 0:
-        raise ValueError("cellparams is empty")
+        parse_d10(recs, cell_f32, cell_i32, layer_f32, layer_i32, layer_rc, np.asarray(idx), parse)
     used = max(1, int(cell_i32[N.HB_NLAY].max()))
     if used < max_layers:
         max_layers = used

@@ -83,6 +83,14 @@ class HelpEngine:
         out["years"] = b.years.astype(np.uint16)
         return out
 
+    def fetch_by_cell(self) -> np.ndarray:
+        """The monthly result as the reference hands it out, one block per cell: float32 [n_cells][7][n_years][12]
+        (rows ``KEYS``), transposed on the device."""
+        b = self.batch
+        out = np.empty((b.n_cells, N.HR_NROWS, b.n_years, 12), dtype=np.float32)
+        N.check(N.lib().help_b200_engine_fetch_monthly_by_cell(self._h, N.ptr(out)), "fetch_monthly_by_cell")
+        return out
+
     def select_daily(self, cells):
         """Ask the next :meth:`simulate` to record the reference's daily output columns (OUTDAY,
         ``HELP3O.FOR:5984-6029``; ``read_daily_help_output``, ``pyhelp/processing.py:150-220``)
@@ -190,9 +198,9 @@ def run_batch_devices(batch: CellBatch, n_devices: int, monthly: bool = True) ->
 
 
 def split_by_cell(batch: CellBatch, res: dict) -> dict:
-    """[row][year][month][cell] -> the reference's dict of per-cell dicts."""
+    """[row][year][month][cell] (or the already cell-major ``res["by_cell"]``) -> the reference's dict of per-cell dicts."""
     years = res["years"]
-    per_cell = np.ascontiguousarray(np.transpose(res["monthly"], (3, 0, 1, 2)))   # (n, 7, ny, 12)
+    per_cell = res["by_cell"] if "by_cell" in res else np.ascontiguousarray(np.transpose(res["monthly"], (3, 0, 1, 2)))   # (n, 7, ny, 12)
     out = {}
     for i, name in enumerate(batch.names):
         d = {"years": years.copy()}
@@ -208,10 +216,15 @@ def run_help_allcells(cellparams: dict, ncore=None) -> dict:
     if len(cellparams) == 0:
         return {}
     N.require_device()          # fail before any host work: this path has no CPU fallback
-    batch = batch_from_cellparams(cellparams)
+    batch = batch_from_cellparams(cellparams, parse="device")      # formatted reads of all records in a few kernels
     want = os.environ.get("HELP_B200_DEVICES", "1")      # "all" or a count: fan out over several GPUs of this process
     ndev = N.lib().help_b200_device_count() if want.strip().lower() == "all" else int(want)
-    res = run_batch_devices(batch, ndev, monthly=True) if ndev > 1 else run_batch(batch, monthly=True)
+    if ndev > 1:
+        res = run_batch_devices(batch, ndev, monthly=True)
+    else:
+        with HelpEngine(batch, monthly=True) as eng:
+            eng.simulate()
+            res = {"years": batch.years.astype(np.uint16), "by_cell": eng.fetch_by_cell()}
     output = split_by_cell(batch, res)
     print("\nTask completed in %0.2f sec" % (time.perf_counter() - tstart))
     return output

@@ -29,6 +29,7 @@ static inline int __any_sync(unsigned, int p) { return p; }
 static inline unsigned __activemask() { return 1u; }
 static inline void __syncthreads() {}
 static inline int __syncthreads_or(int p) { return p; }
+static inline int atomicAdd(int* p, int v) { int o = *p; *p += v; return o; }
 static inline float __fmul_rn(float a, float b) { return a * b; }
 static inline float __fadd_rn(float a, float b) { return a + b; }
 #include <math.h>

@@ -45,8 +45,8 @@ extern "C" int emu_run(const help_b200_batch* b, float* monthly, float* yearly, 
   std::vector<float> f32(Image::n_f32(segcap) * stride); std::vector<int32_t> i32(Image::n_i32(segcap) * stride); std::vector<double> f64(Image::n_f64(segcap) * stride);
   std::vector<char> rec((size_t)Image::rec_bytes(stride, segcap));
   Image img{f32.data(), i32.data(), f64.data(), stride, segcap, rec.data()};
-  for (int64_t c = 0; c < n; ++c) { blockIdx.x = (unsigned)c; help_setup_kernel(B, img, nullptr, flags, topo, nullptr); }
-  SimArgs A; A.img = img; A.pre = pre.data(); A.tmp = tmp.data(); A.rad = rad.data(); A.years = b->years; A.n_years = ny; A.n_cells = n; A.perm = nullptr;
+  for (int64_t c = 0; c < n; ++c) { blockIdx.x = (unsigned)c; help_setup_kernel(B, img, nullptr, flags, topo, nullptr, nullptr); }
+  SimArgs A; A.img = img; A.pre = pre.data(); A.tmp = tmp.data(); A.rad = rad.data(); A.years = b->years; A.n_years = ny; A.n_cells = n; A.first = 0; A.count = n; A.perm = nullptr;
   A.monthly = monthly; A.yearly = yearly; A.raw = raw; A.flags = flags; std::vector<int32_t> drow(n); for (int64_t c = 0; c < n; ++c) drow[c] = (int32_t)c;
   A.daily = g_daily; A.daily_row = g_daily ? drow.data() : nullptr; A.daily_days = g_daily_days;
 #ifdef HELP_DBG_CAPMEMO

@@ -50,3 +50,47 @@ def test_batch_from_grid_device_weather_gives_the_same_batch():
     b = G.batch_from_grid(g, wx["years_of_day"], wx["precip"], wx["airtemp"], wx["solrad"], node, node, node, weather="device")
     for k in ("years", "pre", "tmp", "rad", "idfs", "cell_f32", "cell_i32", "layer_f32", "layer_i32", "layer_rc"):
         assert np.array_equal(getattr(a, k), getattr(b, k)), k
+
+
+def test_device_formatted_read_equals_host_read(tmp_path, rcra_dir):
+    """help_b200_parse_fields (csrc/help_parse.cuh) vs the host's conversion of the same fixed-width fields: hand-made
+    records with every form a Fortran input field takes, then the records and weather files of RCRA and of a synthetic
+    landfill grid through batch_from_cellparams(parse='device')."""
+    import os.path as osp
+    from pyhelp_b200 import inputs
+    fields = ["      ", "  12.5", " -0.25", "+3    ", "  1 2 ", "1.5E+3", "1.5D-2", "12E1  ", " 125  ", ".5    ", "5.    ", "-.5e-2", "1.5+2 ",
+              "123456", "0.0001", "  -0  ", "9.9999", "000001", "1e22  ", "1e-22 ", "1e23  ", "7E0   "]
+    rec = inputs._records(np.array(["".join(fields)]), reclen=6 * len(fields))
+    specs = [(6 * k, 6, 2) for k in range(len(fields))]
+    host = []
+    for k, f in enumerate(fields):                                      # Fortran semantics, field by field
+        t = f.replace(" ", "")
+        if not t:
+            host.append(0.0); continue
+        t2 = t.upper().replace("D", "E")
+        if "E" not in t2 and ("+" in t2[1:] or "-" in t2[1:]):
+            i = max(t2.rfind("+"), t2.rfind("-")); t2 = t2[:i] + "E" + t2[i:]
+        mant = t2.split("E")[0]
+        v = float(t2)
+        host.append(v / 100.0 if "." not in mant else v)
+    dev = inputs.parse_matrix(rec, specs, "device")[:, 0]
+    assert np.array_equal(dev, np.array(host)), list(zip(fields, dev.tolist(), host))
+    with pytest.raises(ValueError):
+        inputs.parse_matrix(inputs._records(np.array(["  1x3 "]), reclen=6), [(0, 6, 0)], "device")
+    # 19 significant digits: flagged by the kernel, converted on the host
+    long = inputs.parse_matrix(inputs._records(np.array(["0.1234567890123456789"]), reclen=21), [(0, 21, 0)], "device")
+    assert long[0, 0] == 0.1234567890123456789
+    # whole inputs: same batch from both paths
+    d10 = np.char.ljust(open(osp.join(rcra_dir, "RCRA.D10")).read().splitlines(), 80).astype("S80")
+    d11 = np.char.ljust(open(osp.join(rcra_dir, "RCRA.D11")).read().splitlines(), 80).astype("S80")
+    cps = [{"rcra": (osp.join(rcra_dir, "RCRA.D4"), osp.join(rcra_dir, "RCRA.D7"), osp.join(rcra_dir, "RCRA.D13"), d11, d10, "x", 0, 1, 0, 0, 3, 32.0)}]
+    g, ex = synth.grid_special(96, seed=8)
+    wx = synth.synth_weather(5, 2003, 2, seed=9)
+    files = synth.write_weather_files(str(tmp_path), wx)
+    node = synth.assign_nodes(96, 5)
+    cps.append(synth.cellparams_from_grid(g, files, node, node, node, 2, tfsoil_c=-3.0, ex=ex))
+    for cp in cps:
+        a, b = inputs.batch_from_cellparams(cp, parse="host"), inputs.batch_from_cellparams(cp, parse="device")
+        for k in ("years", "pre", "tmp", "rad", "iu4", "iu7", "iu13", "tm_normals", "idfs", "cell_f32", "cell_i32", "layer_f32", "layer_i32", "layer_rc"):
+            x, y = getattr(a, k), getattr(b, k)
+            assert x.dtype == y.dtype and np.array_equal(x, y), k
