@@ -24,6 +24,8 @@ NVCC_FLAGS = [
     # every REAL*4 / REAL*8 operation rounds once, as in the reference's SSE2 code;
     # contraction into FMA would move results away from the oracle (DESIGN.md "Numerics")
     "-fmad=false",
+    # the simulation kernel is compiled in 13 instantiations of ~300 KB of SASS each: one ptxas job per kernel, in parallel
+    "-split-compile", "0",
     "-Xcompiler", "-fPIC", "-shared",
 ]
 

@@ -313,22 +313,6 @@ static void launch_sim(const SimArgs& A, cudaStream_t st) {
 // One launch of image slots [A.first, A.first + A.count) with the instantiation for `maxseg_t` segments;
 // the 16-segment one comes in four register budgets (pick_shape).
 static int launch_tier(const SimArgs& A, int maxseg_t, int device, cudaStream_t st) {
-#ifdef HELP_AB_BIGREG
-  // developer A/B: a launch that cannot fill a quarter of the SMs' thread slots runs with every register a thread can
-  // have (255: no spills) in 64-thread blocks
-  {
-    int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-    if ((A.count + sms - 1) / sms <= 256) {
-      switch (maxseg_t) {
-        case 16: launch_sim<16, 64, 255>(A, st); return 0;
-        case 25: launch_sim<25, 64, 255>(A, st); return 0;
-        case 40: launch_sim<40, 64, 255>(A, st); return 0;
-        default: break;
-      }
-    }
-  }
-#endif
   switch (maxseg_t) {
     case 16:
       switch (pick_shape(A.count, device)) {
@@ -348,10 +332,12 @@ static int launch_tier(const SimArgs& A, int maxseg_t, int device, cudaStream_t 
   }
 }
 
-// Launch plan (HELP_B200_PLAN overrides: 0 = one launch of the widest instantiation, 1 = narrow tier first,
-// 2 = wide tier first).  The sort puts the narrow tier -- plain profiles of at most 16 segments, i.e. every
-// natural-soil cell -- in front; when a batch also holds liner profiles the two tiers are launched separately,
-// each with its own instantiation, on two streams so that the second fills the SMs as the first drains.
+// Launch plan.  The sort puts the narrow tier -- plain profiles of at most 16 segments, i.e. every natural-soil cell --
+// in front.  A batch that holds nothing else runs the 16-segment instantiation whatever its deepest profile would allow
+// (a shard of a class-sorted grid, pyhelp_b200.sharding.plan_shards, is such a batch).  A batch that also holds liner
+// profiles runs ONE launch of the widest instantiation: launching the tiers separately (HELP_B200_PLAN = 1: narrow first,
+// 2: wide first, on two streams) was measured slower in round 1 and again in round 2 (125 000 mixed cells x 6 simulated
+// years: 1238 / 1361 / 1618 ms, profiles/r2_plan_ab.log) -- the wide tier alone cannot fill the SMs and becomes the tail.
 extern "C" int help_b200_engine_simulate(help_b200_engine* e, void* stream) {
   if (!e) return fail(HELP_B200_EINVAL, "engine is NULL");
   CU(cudaSetDevice(e->device));
@@ -384,7 +370,7 @@ extern "C" int help_b200_engine_simulate(help_b200_engine* e, void* stream) {
     A.n_years = e->ny; A.n_cells = n; A.first = 0; A.count = n; A.perm = perm;
     A.monthly = e->d_monthly; A.yearly = e->d_yearly; A.raw = e->d_raw; A.flags = e->d_flags;
     A.daily = e->d_daily; A.daily_row = e->d_daily_row; A.daily_days = e->daily_days;
-    int plan = 1;
+    int plan = 0;
     if (const char* f = getenv("HELP_B200_PLAN")) plan = atoi(f);
     int rc = 0;
     if (n_narrow == n && e->sort) {
