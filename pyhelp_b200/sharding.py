@@ -21,11 +21,11 @@ def shard_range(n_cells: int, world: int, rank: int) -> tuple[int, int]:
     return start, start + base + (1 if rank < rem else 0)
 
 
-# Relative cost of a cell by profile structure, per modelling segment (calibrated on B200: per-rank
-# kernel times of class-sorted shards of BASELINE configs[2]/[3], profiles/r2_notes.md): a profile
-# with a liner pays head, leakage and lateral-drainage iterations every sub-step and runs more
-# sub-steps per day.
-COST_LINER = 3.0
+# Relative cost of a cell by profile structure, per modelling segment: a profile with a liner pays
+# head, leakage and lateral-drainage iterations every sub-step.  Calibrated on B200 with the per-rank
+# kernel times of a class-sorted 1 M-cell BASELINE configs[2] grid on 2 GPUs (profiles/r2_notes.md:
+# 752 826 mostly plain cells 24.0 s, 247 174 liner cells 17.9 s with a factor of 3 => 2.1).
+COST_LINER = 2.1
 
 
 def _segments(nlay, thick_in, on):

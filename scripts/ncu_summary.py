@@ -36,6 +36,20 @@ for k, r in enumerate(sim):
 os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
 open(os.path.join(ROOT, "profiles", tag + "_metrics.txt"), "w").write("\n".join(out) + "\n")
 print("\n".join(out))
+if "--limits" in sys.argv:            # the counters that bound the kernel, from this capture alone (no DRAM-byte claim)
+    r = sim[-1]
+    def num(name):
+        try: return float(r[hdr.index(name)])
+        except (ValueError, IndexError): return None
+    lim = {"source": "profiles/%s_metrics.txt (ncu --set full of %s)" % (tag, os.path.basename(rep)),
+           "fp64_pipe_pct_of_peak": num("sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"),
+           "issue_slots_active_pct": num("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+           "lanes_active_of_32": num("smsp__thread_inst_executed_per_inst_executed.ratio"),
+           "warps_active_per_sm": num("sm__warps_active.avg.per_cycle_active"),
+           "l2_hit_pct": num("lts__t_sector_hit_rate.pct"), "l1_hit_pct": num("l1tex__t_sector_hit_rate.pct"),
+           "top_stalls_per_issue": {k: num("smsp__average_warps_issue_stalled_%s_per_issue_active.ratio" % k)
+                                    for k in ("long_scoreboard", "wait", "no_instruction", "not_selected", "barrier")}}
+    json.dump(lim, open(os.path.join(ROOT, "profiles", tag + "_limits.json"), "w"), indent=1)
 if "--traffic" in sys.argv:
     r = sim[-1]
     def val(name):
@@ -74,6 +88,15 @@ for r in csv.reader(io.StringIO(src)):
                         int(d["Thread Instructions Executed"]), int(d["stall_long_sb"]), int(d["stall_wait"]), int(d["stall_barrier"])))
         except (ValueError, KeyError):
             pass
+def repo_line(fname, line):
+    """the text of that line in the committed source (exposes a report whose line numbers belong to another revision)"""
+    for d in ("pyhelp_b200/csrc", "include"):
+        p = os.path.join(ROOT, d, fname or "")
+        if os.path.exists(p):
+            L = open(p, errors="replace").read().splitlines()
+            return L[line - 1].strip()[:80] if 0 < line <= len(L) else "<beyond end of file>"
+    return None
+acc = [(o[0], o[1], repo_line(o[0], o[1]) or o[2]) + o[3:] for o in acc]
 if acc:
     ts = sum(o[3] for o in acc) or 1; ti = sum(o[4] for o in acc) or 1
     L = ["# per source line: %% of stall samples, %% of warp instructions, active lanes, of which long-scoreboard / fixed-latency wait / barrier (%% of samples)"]
