@@ -21,7 +21,7 @@ One JSON line (rank 0):
   other_configs  (N=1) configs[2] and [3] at the size one GPU carries: 125 000 mixed-class cells x
                  30 yr and 31 250 landfill covers x 50 yr, each with its own roofline
   target         (N>1) ONE configs[2] grid -- 1 M mixed-class cells, 10 000 weather nodes, 30 yr --
-                 partitioned by pyhelp_b200.sharding (class-sorted, cost-balanced), simulated, yearly
+                 partitioned by pyhelp_b200.sharding (class-sorted list dealt out over the ranks), simulated, yearly
                  summaries NCCL-gathered to rank 0 in the caller's order: wall time, per-rank
                  kernel times, imbalance
   roofline, cpu_baseline, clocks, gpu_launches as the contract asks.
@@ -320,7 +320,7 @@ def one_config(kind: str, n: int, ny: int, seed: int, N):
 def run_target(world, rank, dev, N, dist, torch):
     """BASELINE configs[2] as `north_star` states the goal: ONE grid of 1 M mixed-class cells with 10 000
     weather nodes, 30 yr, partitioned over the ranks by the product's own sharding code
-    (pyhelp_b200.sharding: class-sorted, cost-balanced contiguous cuts), packed per rank, simulated,
+    (pyhelp_b200.sharding: class-sorted list dealt out over the ranks, every rank the same share of every class), packed per rank, simulated,
     yearly summaries gathered to rank 0 over NCCL and put back in the caller's cell order.
     Every rank holds the caller's tables (as every rank would read the same grid/weather files)."""
     from pyhelp_b200 import grid as G, processing, sharding
@@ -395,7 +395,7 @@ def run_target(world, rank, dev, N, dist, torch):
         "imbalance": float(kms.max() / kms.mean()),
         "gather_ms": float(A[0, 4] * 1e3), "cells_flagged_nan_or_bad": int(A[:, 9].sum()),
         "caller_order_restored": bool(ok),
-        "partition": "pyhelp_b200.sharding.grid_cost_and_class + plan_shards (class-sorted, cost-balanced), gather_yearly, restore_order",
+        "partition": "pyhelp_b200.sharding.grid_cost_and_class + plan_shards (class-sorted grid dealt out over the ranks: every rank the same share of every class), gather_yearly, restore_order",
     }
 
 

@@ -305,27 +305,53 @@ static int pick_shape(int64_t n, int device) {
   return 3;
 }
 
-template <int MAXSEG, int THREADS, int REGS>
-static void launch_sim(const SimArgs& A, cudaStream_t st) {
-  help_sim_kernel<MAXSEG, THREADS, REGS><<<(unsigned)((A.count + THREADS - 1) / THREADS), THREADS, 0, st>>>(A);
+// Threads per block = the warps that share the day barrier of help_sim_kernel.  Plain (natural-soil) profiles run best in
+// blocks of 128 (larger groups wait longer at the barrier: 100 000 cells 684 / 686 / 699 / 759 ms for blocks of 128 / 256 /
+// 352 / 704).  The routing code of a profile with a liner is larger than the instruction cache, so the warps of an SM should
+// fetch it together: ONE block per SM, as wide as the batch fills the SMs in evenly filled waves (125 000 mixed cells 1181 /
+// 1002 / 966 ms for 128 / 256 / 512; 31 250 landfill covers 810 / 776 ms for 128 / 224; profiles/r2_notes.md).
+enum LaunchKind : int { kPlainOnly = 0, kLinerOnly = 1, kMixed = 2 };   // profile classes of a launch
+static int pick_block(int64_t n, int cap, int kind, int device) {
+  if (const char* f = getenv("HELP_B200_BLOCK")) { const int v = atoi(f); if (v >= 32 && v <= cap) return v; }
+  if (kind == kPlainOnly) return 128;
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  const int64_t per = (n + sms - 1) / sms;                      // threads per SM
+  // plain and liner profiles in one launch: the liner blocks (launched first, several times the run time of a plain one) are
+  // the critical path, plain blocks fill in behind them -- the widest block (448: 1013 ms, 512: 964 ms for 125 000 mixed cells)
+  if (kind == kMixed && per > cap) return cap;
+  const int64_t waves = (per + cap - 1) / cap;
+  const int64_t per_wave = (per + waves - 1) / (waves > 0 ? waves : 1);
+  int64_t b = (per_wave + 31) / 32 * 32;
+  if (b < 128) b = 128;
+  if (b > cap) b = cap;
+  return (int)b;
+}
+
+// CAP = threads per SM the register budget keeps resident = the largest block the instantiation accepts.
+template <int MAXSEG, int CAP, int REGS>
+static void launch_sim(const SimArgs& A, cudaStream_t st, int kind, int device) {
+  const int block = pick_block(A.count, CAP, kind, device);
+  help_sim_kernel<MAXSEG, CAP, REGS><<<(unsigned)((A.count + block - 1) / block), block, 0, st>>>(A);
 }
 
 // One launch of image slots [A.first, A.first + A.count) with the instantiation for `maxseg_t` segments;
 // the 16-segment one comes in four register budgets (pick_shape).
-static int launch_tier(const SimArgs& A, int maxseg_t, int device, cudaStream_t st) {
+static int launch_tier(const SimArgs& A, int maxseg_t, int device, cudaStream_t st, int kind) {
   switch (maxseg_t) {
     case 16:
       switch (pick_shape(A.count, device)) {
-        case 0: launch_sim<16, 128, 128>(A, st); break;
-        case 1: launch_sim<16, 128, 96>(A, st); break;
-        case 2: launch_sim<16, 128, 80>(A, st); break;
-        default: launch_sim<16, 128, 64>(A, st); break;
+        case 0: launch_sim<16, 512, 128>(A, st, kind, device); break;
+        case 1: launch_sim<16, 640, 96>(A, st, kind, device); break;
+        case 2: launch_sim<16, 768, 80>(A, st, kind, device); break;
+        default: launch_sim<16, 1024, 64>(A, st, kind, device); break;
       }
       return 0;
 #ifndef HELP_DEV_FAST_BUILD
-    case 25: launch_sim<25, 128, 128>(A, st); return 0;
-    case 40: launch_sim<40, 128, 128>(A, st); return 0;
-    default: launch_sim<67, 128, 128>(A, st); return 0;
+    // (96 / 80 registers for the wide tiers: 125 000 mixed cells 974 -> 1007 / 1108 ms, profiles/r2_notes.md)
+    case 25: launch_sim<25, 512, 128>(A, st, kind, device); return 0;
+    case 40: launch_sim<40, 512, 128>(A, st, kind, device); return 0;
+    default: launch_sim<67, 512, 128>(A, st, kind, device); return 0;
 #else
     default: return fail(HELP_B200_EINVAL, "developer build: MAXSEG 16 only");
 #endif
@@ -374,10 +400,10 @@ extern "C" int help_b200_engine_simulate(help_b200_engine* e, void* stream) {
     if (const char* f = getenv("HELP_B200_PLAN")) plan = atoi(f);
     int rc = 0;
     if (n_narrow == n && e->sort) {
-      rc = launch_tier(A, 16, e->device, st);                       // every cell is narrow, whatever max_layers says
+      rc = launch_tier(A, 16, e->device, st, kPlainOnly);                     // every cell is narrow, whatever max_layers says
       e->n_launches += 1;
     } else if (plan == 0 || n_narrow == 0 || !e->sort) {
-      rc = launch_tier(A, e->maxseg_t, e->device, st);
+      rc = launch_tier(A, e->maxseg_t, e->device, st, (e->sort && n_narrow > 0) ? kMixed : kLinerOnly);
       e->n_launches += 1;
     } else {
       SimArgs N1 = A, W = A;
@@ -386,11 +412,11 @@ extern "C" int help_b200_engine_simulate(help_b200_engine* e, void* stream) {
       CU(cudaEventRecord(e->ev_fork, st));
       CU(cudaStreamWaitEvent(e->stream2, e->ev_fork, 0));
       if (plan == 2) {
-        rc = launch_tier(W, e->maxseg_t, e->device, st);
-        if (!rc) rc = launch_tier(N1, 16, e->device, e->stream2);
+        rc = launch_tier(W, e->maxseg_t, e->device, st, kLinerOnly);
+        if (!rc) rc = launch_tier(N1, 16, e->device, e->stream2, kPlainOnly);
       } else {
-        rc = launch_tier(N1, 16, e->device, st);
-        if (!rc) rc = launch_tier(W, e->maxseg_t, e->device, e->stream2);
+        rc = launch_tier(N1, 16, e->device, st, kPlainOnly);
+        if (!rc) rc = launch_tier(W, e->maxseg_t, e->device, e->stream2, kLinerOnly);
       }
       CU(cudaEventRecord(e->ev_join, e->stream2));
       CU(cudaStreamWaitEvent(st, e->ev_join, 0));

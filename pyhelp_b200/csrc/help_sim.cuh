@@ -581,23 +581,31 @@ struct Surf {      // REAL*4 surface-process state of one cell
 // Block shape.  Every warp of a block is kept in the same day of the simulation by one
 // barrier per day (HELP_SIM_DAYSYNC): the routing code is larger than the 32 KB L1.5
 // instruction cache, and warps that run the same region together share its fetches
-// (measured on B200: +12 % throughput, profiles/r1_notes.md).
-// The kernel is compiled for several launch shapes (THREADS per block, REGS per thread ->
-// resident threads per SM: 128-thread blocks at 128 registers = 512, at 96 = 640, at 80 = 768, at
-// 64 = 1024; the per-cell cost is flat from 640 threads up, so what matters is one full wave): all cells of a launch take the same time, so the launcher (help_capi.cu pick_shape)
-// chooses the shape with the most registers that still fits the batch into the fewest,
-// evenly filled waves.
+// (measured on B200: 100 000 natural cells 716 ms with the barrier, 838 ms without; profiles/r2_notes.md).
+// The kernel is compiled for several register budgets (CAP = threads per SM a budget keeps resident =
+// the largest block of the instantiation: 128 registers -> 512, 96 -> 640, 80 -> 768, 64 -> 1024).
+// All cells of a launch take about the same time, so the launcher (help_capi.cu) chooses the budget
+// with the most registers that still fits the batch into the fewest, evenly filled waves (pick_shape),
+// and the block size by profile class (pick_block): 128 threads for plain profiles, one block per SM
+// for batches with liner profiles, whose routing code does not fit the instruction cache.
 #ifndef HELP_SIM_NO_DAYSYNC
 #define HELP_SIM_DAYSYNC 1
 #endif
-template <int MAXSEG, int THREADS, int REGS>
-__global__ void __launch_bounds__(THREADS) __maxnreg__(REGS) help_sim_kernel(SimArgs A) {
+template <int MAXSEG, int CAP, int REGS>
+__global__ void __launch_bounds__(CAP) __maxnreg__(REGS) help_sim_kernel(SimArgs A) {
   helpmath::hm_load_tables();
   // No thread leaves before the end: the day barrier below must be reached by every thread of the
   // block the same number of times.  A thread past the end of the batch, or one whose cell cannot
   // be simulated, reads the last cell's constants (valid addresses) and sits out every day
   // (`live == false`); it only keeps the barrier count.
+#ifndef HELP_FWD_BLOCKS
+  // The sort key ascends with the cost of a cell and the hardware hands out blocks in index order: the last blocks -- the ones
+  // that land on SMs which already hold a full share, and the tail of a launch with more blocks than the GPU keeps resident --
+  // must be the cheapest.  Measured on B200: 100 000 natural cells 5.2 % faster, 125 000 mixed cells 8.6 % (profiles/r2_notes.md).
+  const int64_t s_raw = (int64_t)(gridDim.x - 1 - blockIdx.x) * blockDim.x + threadIdx.x;
+#else
   const int64_t s_raw = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+#endif
   bool live = s_raw < A.count;
   const int64_t s = A.first + (live ? s_raw : A.count - 1);
   const Image& img = A.img;

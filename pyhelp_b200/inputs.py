@@ -20,6 +20,8 @@ from __future__ import annotations
 import os
 from dataclasses import dataclass, field
 
+import re
+
 import numpy as np
 
 from . import _native as N
@@ -45,11 +47,20 @@ def _to_real(txt: np.ndarray, d: int, dtype) -> np.ndarray:
             vals = t.astype(np.float64)                 # plain decimal fields: the usual case
         except ValueError:                              # embedded blanks (ignored, BN) or a D exponent
             t = np.char.replace(np.char.replace(np.char.replace(t, b" ", b""), b"D", b"E"), b"d", b"e")
-            vals = t.astype(np.float64)
+            try:
+                vals = t.astype(np.float64)
+            except ValueError:                          # "1.5+2": an exponent without its letter
+                t = np.array([re.sub(rb"(?<=[0-9.])([+-])", rb"E\1", x, count=1) if b"E" not in x.upper() else x for x in t])
+                vals = t.astype(np.float64)
         if d > 0:
             nodot = np.char.find(t, b".") < 0          # Fw.d: no point -> the last d digits of the significand are decimals, exponent or not
             if nodot.any():
-                vals[nodot] = vals[nodot] / (10.0 ** d)
+                vals[nodot] = vals[nodot] / (10.0 ** d)  # an integer below 2^53 over a power of ten: one rounding
+                # with an exponent the value read above is already rounded: convert significand x 10^(exponent - d)
+                # in one step, as libgfortran does (and csrc/help_parse.cuh)
+                for i in np.nonzero(nodot & (np.char.find(np.char.upper(t), b"E") >= 0))[0]:
+                    mant, _, ex = t[i].decode().upper().partition("E")
+                    vals[i] = float(f"{mant}E{int(ex) - d}")
         out[nz] = vals
     return out.astype(dtype)
 

@@ -1,13 +1,17 @@
 """Multi-GPU sharding of a cell batch: one process per GPU, no data-path collective.
 
 The reference's only parallelism is data parallel over independent cells
-(``Pool(ncore).imap_unordered``, reference ``pyhelp/processing.py:40-59``).  Here the cells are cut
-into contiguous, equally sized shards (one per rank); each rank uploads only the weather nodes
-its cells reference, simulates, and the per-cell yearly summaries ``[5][Ny][n_local]`` are
-gathered to rank 0 -- over NCCL (NVLink) on GPUs, over gloo in the CPU tests.  Nothing is
-exchanged during the simulation itself.
+(``Pool(ncore).imap_unordered``, reference ``pyhelp/processing.py:40-59``).  Here one grid is
+sorted by profile class and dealt out over the ranks (``plan_shards``: every rank the same share of
+every class) or, for an already packed batch, cut into contiguous shards (``shard_batch``); each
+rank uploads only the weather nodes its cells reference, simulates, and the per-cell yearly
+summaries ``[5][Ny][n_local]`` are gathered to rank 0 -- over NCCL (NVLink) on GPUs, over gloo in
+the CPU tests -- and put back in the caller's cell order.  Nothing is exchanged during the
+simulation itself.
 """
 from __future__ import annotations
+
+import os
 
 import numpy as np
 
@@ -21,11 +25,13 @@ def shard_range(n_cells: int, world: int, rank: int) -> tuple[int, int]:
     return start, start + base + (1 if rank < rem else 0)
 
 
-# Relative cost of a cell by profile structure, per modelling segment: a profile with a liner pays
-# head, leakage and lateral-drainage iterations every sub-step.  Calibrated on B200 with the per-rank
-# kernel times of a class-sorted 1 M-cell BASELINE configs[2] grid on 2 GPUs (profiles/r2_notes.md:
-# 752 826 mostly plain cells 24.0 s, 247 174 liner cells 17.9 s with a factor of 3 => 2.1).
-COST_LINER = 2.1
+# Relative cost of a cell by profile structure, per modelling segment: a profile with a liner pays head, leakage and
+# lateral-drainage iterations every sub-step and runs the larger routing code.  Measured on B200 (scripts/class_cost.py,
+# the four classes of the BASELINE configs[2] grid on their own, 100 000 cells each: 0.116 / 0.118 us per cell-year and
+# segment for the two natural classes, 0.228 / 0.224 for the two liner classes => 1.9).  The ratio holds when every class
+# fills the GPU; a rank that holds fewer liner cells than the SMs keep resident is latency-bound and the ratio drops to
+# ~1.55 -- which is why plan_shards deals the classes out instead of relying on this number.
+COST_LINER = float(os.environ.get("HELP_B200_COST_LINER", 1.9))
 
 
 def _segments(nlay, thick_in, on):
@@ -74,18 +80,31 @@ def grid_cost_and_class(grid: dict):
     return cost, (2 * tier + liner.astype(np.int64))
 
 
-def plan_shards(cost, klass, world: int, node=None):
-    """Partition of one grid over ``world`` ranks: cells stably sorted by (class,
-    cost, weather node), the sorted list cut into contiguous runs of equal total cost.  Returns
-    ``(order, ranges)``: rank r simulates the cells ``order[ranges[r][0]:ranges[r][1]]``.  Ranks then
-    hold (nearly) one profile class each, so each engine picks the kernel instantiation of its own
-    shard, and every rank finishes at the same time although a liner profile costs several natural
-    ones."""
+def plan_shards(cost, klass, world: int, node=None, mode: str = "deal"):
+    """Partition of one grid over ``world`` ranks.  The cells are stably sorted by (class, cost, weather
+    node); returns ``(order, ranges)``: rank r simulates the cells ``order[ranges[r][0]:ranges[r][1]]``.
+
+    ``mode="deal"`` (default): the sorted list is dealt out card by card -- rank r takes every ``world``-th cell starting
+    at r -- so every rank holds the same number of cells of every class and the same cost distribution: the ranks finish
+    together *by construction*, whatever a class costs on the hardware.  Inside a rank the engine sorts again and launches
+    the expensive classes first.
+
+    ``mode="contiguous"``: the sorted list is cut into contiguous runs of equal estimated cost (ranks then hold nearly one
+    class each).  Measured on B200 with the 1 M-cell BASELINE configs[2] grid cut for 8 ranks: per-shard kernel times
+    differ by 15-19 % (max/mean) however the liner factor is set -- the time of a class depends on how full the SMs of its
+    rank are, not only on its segments -- while the dealt shards run as fast as the mean of the contiguous ones
+    (profiles/r2_notes.md)."""
     cost = np.asarray(cost, dtype=np.float64).reshape(-1)
     keys = [np.zeros(cost.size, dtype=np.int64) if node is None else np.asarray(node).reshape(-1), cost,
             np.asarray(klass).reshape(-1)]
     order = np.lexsort(keys)                                  # last key is the primary one; stable
-    return order, cost_balanced_ranges(cost[order], world)
+    if mode == "contiguous":
+        return order, cost_balanced_ranges(cost[order], world)
+    if mode != "deal":
+        raise ValueError("mode must be 'deal' or 'contiguous'")
+    hands = [order[r::world] for r in range(world)]
+    stops = np.cumsum([h.size for h in hands])
+    return np.concatenate(hands) if hands else order, [(int(b - h.size), int(b)) for h, b in zip(hands, stops)]
 
 
 def restore_order(gathered, order):

@@ -70,9 +70,9 @@ def test_device_formatted_read_equals_host_read(tmp_path, rcra_dir):
         t2 = t.upper().replace("D", "E")
         if "E" not in t2 and ("+" in t2[1:] or "-" in t2[1:]):
             i = max(t2.rfind("+"), t2.rfind("-")); t2 = t2[:i] + "E" + t2[i:]
-        mant = t2.split("E")[0]
-        v = float(t2)
-        host.append(v / 100.0 if "." not in mant else v)
+        mant, _, ex = t2.partition("E")
+        # one correctly rounded conversion of significand x 10^(exponent - d), as libgfortran's READ does
+        host.append(float(t2) if "." in mant else float(f"{mant}E{int(ex or 0) - 2}"))
     dev = inputs.parse_matrix(rec, specs, "device")[:, 0]
     assert np.array_equal(dev, np.array(host)), list(zip(fields, dev.tolist(), host))
     with pytest.raises(ValueError):

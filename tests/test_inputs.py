@@ -138,3 +138,18 @@ def test_idfs_prescan_reads_f61_whatever_the_units(tmp_path):
     assert info["idfs"] == ints.idfs[0]
     # Fw.d without a point: the implied decimals apply to the significand, exponent or not
     assert inputs._to_real(np.array([b"125E1", b"12.5E1", b"125"]), 2, np.float64).tolist() == [12.5, 125.0, 1.25]
+
+
+def test_host_formatted_read_of_every_field_form():
+    """Fw.d input fields as libgfortran reads them (blanks ignored, implied decimals without a point, E/D/bare-sign
+    exponents; one correctly rounded conversion) -- the host leg of parse_matrix; tests/test_gpu_pack.py holds the device
+    leg to the same values."""
+    fields = ["      ", "  12.5", " -0.25", "+3    ", "  1 2 ", "1.5E+3", "1.5D-2", "12E1  ", " 125  ", ".5    ", "5.    ",
+              "-.5e-2", "1.5+2 ", "123456", "0.0001", "  -0  ", "9.9999", "000001", "1e22  ", "1e-22 ", "1e23  ", "7E0   "]
+    want = [0.0, 12.5, -0.25, 0.03, 0.12, 1500.0, 0.015, 1.2, 1.25, 0.5, 5.0, -0.005, 150.0, 1234.56, 0.0001, -0.0, 9.9999,
+            0.01, 1e20, 1e-24, 1e21, 0.07]
+    rec = inputs._records(np.array(["".join(fields)]), reclen=6 * len(fields))
+    got = inputs.parse_matrix(rec, [(6 * k, 6, 2) for k in range(len(fields))], "host")[:, 0]
+    assert np.array_equal(got, np.array(want)) and np.signbit(got[15])
+    with pytest.raises(ValueError):
+        inputs.parse_matrix(inputs._records(np.array(["  1x3 "]), reclen=6), [(0, 6, 0)], "host")

@@ -165,9 +165,10 @@ def test_run_batch_devices_joins_shards_in_caller_order(monkeypatch):
         processing.run_batch_devices(b, 2)
 
 
-def test_grid_plan_is_class_sorted_and_cost_balanced():
-    """sharding.grid_cost_and_class / plan_shards: one grid, class-sorted, cut into runs of equal cost
-     -- from the grid columns alone, and equal to the cost the packed batch gives."""
+def test_grid_plan_deals_every_class_evenly_and_contiguous_plan_is_cost_balanced():
+    """sharding.grid_cost_and_class / plan_shards: one grid, class-sorted, dealt out over the ranks (every rank the
+    same share of every class: SURVEY.md 8e) -- from the grid columns alone, and equal to the cost the packed batch
+    gives; the contiguous variant cuts runs of equal estimated cost."""
     n, world = 4000, 4
     g = synth.grid_mixed(n, seed=2)
     node = synth.assign_nodes(n, 40)
@@ -178,17 +179,30 @@ def test_grid_plan_is_class_sorted_and_cost_balanced():
     order, ranges = sharding.plan_shards(cost, klass, world, node)
     assert np.array_equal(np.sort(order), np.arange(n))
     assert ranges[0][0] == 0 and ranges[-1][1] == n and all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
-    assert (np.diff(klass[order]) >= 0).all()                              # class-major
-    tot = np.array([cost[order[a:b]].sum() for a, b in ranges])
-    assert tot.max() / tot.mean() < 1.01
-    # plain profiles of at most 16 segments first: the first rank needs only the narrow kernel instantiation
-    a, b_ = ranges[0]
-    lt = np.stack([g[f"lay_type{j}"] for j in range(1, 6)])
-    assert (lt[:, order[a:b_]] < 3).all() and g["nlayer"][order[a:b_]].max() <= 3
-    # liner profiles cost more, so their ranks hold fewer cells
-    assert (ranges[-1][1] - ranges[-1][0]) < (ranges[0][1] - ranges[0][0])
+    sizes = [b_ - a for a, b_ in ranges]
+    assert max(sizes) - min(sizes) <= 1
+    for k in np.unique(klass):                                             # every class is shared out evenly ...
+        per = [int((klass[order[a:b_]] == k).sum()) for a, b_ in ranges]
+        assert max(per) - min(per) <= 1
+    for a, b_ in ranges:                                                   # ... and stays sorted inside a rank
+        assert (np.diff(klass[order[a:b_]]) >= 0).all()
+    tot = np.array([cost[order[a:b_]].sum() for a, b_ in ranges])
+    assert tot.max() / tot.mean() < 1.005
     r = sharding.restore_order(np.arange(n, dtype=np.float32)[order][None, :], order)
     assert np.array_equal(r[0], np.arange(n, dtype=np.float32))
+    # contiguous runs of equal estimated cost
+    order, ranges = sharding.plan_shards(cost, klass, world, node, mode="contiguous")
+    assert np.array_equal(np.sort(order), np.arange(n))
+    assert ranges[0][0] == 0 and ranges[-1][1] == n and all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
+    assert (np.diff(klass[order]) >= 0).all()                              # class-major
+    tot = np.array([cost[order[a:b_]].sum() for a, b_ in ranges])
+    assert tot.max() / tot.mean() < 1.01
+    a, b_ = ranges[0]                                                      # plain profiles of at most 16 segments first
+    lt = np.stack([g[f"lay_type{j}"] for j in range(1, 6)])
+    assert (lt[:, order[a:b_]] < 3).all() and g["nlayer"][order[a:b_]].max() <= 3
+    assert (ranges[-1][1] - ranges[-1][0]) < (ranges[0][1] - ranges[0][0])  # liner profiles cost more: fewer cells per rank
+    with pytest.raises(ValueError):
+        sharding.plan_shards(cost, klass, world, node, mode="x")
 
 
 def _plan_worker(rank, world, port, n_total, q):
@@ -209,7 +223,7 @@ def _plan_worker(rank, world, port, n_total, q):
 
 
 def test_planned_shards_gather_to_caller_order_gloo_world2():
-    """the N>1 path of bench.py's `target` on CPU: unequal, class-sorted shards, gathered over gloo and
+    """the N>1 path of bench.py's `target` on CPU: unequal shards of a class-sorted grid, gathered over gloo and
     put back in the caller's cell order"""
     n_total = 301
     ctx = mp.get_context("spawn")
@@ -222,7 +236,7 @@ def test_planned_shards_gather_to_caller_order_gloo_world2():
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
-    assert (ranges[0][1] - ranges[0][0]) != (ranges[1][1] - ranges[1][0])
+    assert (ranges[0][1] - ranges[0][0]) != (ranges[1][1] - ranges[1][0])      # 301 cells: 151 + 150
     want = (np.arange(n_total, dtype=np.float32)[None, None, :] + 1000.0 * np.arange(5)[:, None, None]
             + 10.0 * np.arange(2)[None, :, None])
     assert np.array_equal(got, want)
