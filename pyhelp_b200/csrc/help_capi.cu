@@ -295,7 +295,7 @@ static const int kShapeCap[4] = {512, 640, 768, 1024};
 // The shape for a batch of n cells: the fewest waves the largest shape allows, filled evenly,
 // with the most registers that still fit.  HELP_B200_SHAPE overrides (developer A/B runs).
 static int pick_shape(int64_t n, int device) {
-  if (const char* f = getenv("HELP_B200_SHAPE")) { const int v = atoi(f); if (v >= 0 && v <= 4) return v; }
+  if (const char* f = getenv("HELP_B200_SHAPE")) { const int v = atoi(f); if (v >= 0 && v <= 3) return v; }
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
   const int64_t need = (n + sms - 1) / sms;                     // threads per SM
@@ -338,22 +338,20 @@ static void launch_sim(const SimArgs& A, cudaStream_t st, int kind, int device) 
 // One launch of image slots [A.first, A.first + A.count) with the instantiation for `maxseg_t` segments;
 // the 16-segment one comes in four register budgets (pick_shape).
 static int launch_tier(const SimArgs& A, int maxseg_t, int device, cudaStream_t st, int kind) {
-  const bool big = getenv("HELP_B200_BIGREG") != nullptr;
   switch (maxseg_t) {
     case 16:
       switch (pick_shape(A.count, device)) {
         case 0: launch_sim<16, 512, 128>(A, st, kind, device); break;
         case 1: launch_sim<16, 640, 96>(A, st, kind, device); break;
         case 2: launch_sim<16, 768, 80>(A, st, kind, device); break;
-        case 3: launch_sim<16, 1024, 64>(A, st, kind, device); break;
-        default: launch_sim<16, 256, 255>(A, st, kind, device); break;
+        default: launch_sim<16, 1024, 64>(A, st, kind, device); break;
       }
       return 0;
 #ifndef HELP_DEV_FAST_BUILD
     // (96 / 80 registers for the wide tiers: 125 000 mixed cells 974 -> 1007 / 1108 ms, profiles/r2_notes.md)
-    case 25: if (big) launch_sim<25, 256, 255>(A, st, kind, device); else launch_sim<25, 512, 128>(A, st, kind, device); return 0;
-    case 40: if (big) launch_sim<40, 256, 255>(A, st, kind, device); else launch_sim<40, 512, 128>(A, st, kind, device); return 0;
-    default: if (big) launch_sim<67, 256, 255>(A, st, kind, device); else launch_sim<67, 512, 128>(A, st, kind, device); return 0;
+    case 25: launch_sim<25, 512, 128>(A, st, kind, device); return 0;
+    case 40: launch_sim<40, 512, 128>(A, st, kind, device); return 0;
+    default: launch_sim<67, 512, 128>(A, st, kind, device); return 0;
 #else
     default: return fail(HELP_B200_EINVAL, "developer build: MAXSEG 16 only");
 #endif
