@@ -224,3 +224,29 @@ def test_six_subprofiles_and_f73_overflow(tmp_path):
     b = inputs.batch_from_cellparams({"overflow": cases["overflow"]})
     r = processing.run_batch(b)
     assert r["flags"][0] & N.FLAG_OVERFLOW and np.isnan(r["monthly"][N.HR_PRECIP]).sum() == 1
+
+
+def test_launch_plan_does_not_change_a_bit(monkeypatch):
+    """The launch plan of help_sim_kernel (help_capi.cu: register budget by batch size, block size by profile class,
+    blocks in descending cost order) decides which SM simulates a cell and with whom it shares its day barrier, never
+    what the cell computes: every override gives the bits of the default plan (which the families above hold to the oracle)."""
+    n, nn, ny = 700, 7, 2
+    g = synth.grid_mixed(n, seed=4)
+    wx = synth.synth_weather(nn, 2003, ny, seed=6)
+    node = synth.assign_nodes(n, nn)
+    b = G.batch_from_grid(g, wx["years_of_day"], wx["precip"], wx["airtemp"], wx["solrad"], node, node, node, tfsoil_c=-3.0)
+    ref = processing.run_batch(b, monthly=True)
+    assert int((ref["flags"] & (N.FLAG_NAN | N.FLAG_BADCELL)).astype(bool).sum()) == 0
+    plain = G.batch_from_grid(synth.grid_natural_3layer(n, seed=4), wx["years_of_day"], wx["precip"], wx["airtemp"], wx["solrad"],
+                              node, node, node, tfsoil_c=-3.0)
+    ref_plain = processing.run_batch(plain, monthly=True)
+    for env in ({"HELP_B200_BLOCK": "32"}, {"HELP_B200_BLOCK": "512"}, {"HELP_B200_BLOCK": "96", "HELP_B200_SHAPE": "3"},
+                {"HELP_B200_SHAPE": "0"}, {"HELP_B200_SHAPE": "1"}, {"HELP_B200_SORT": "0"}, {"HELP_B200_PLAN": "1"}):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        for batch, want in ((b, ref), (plain, ref_plain)):
+            got = processing.run_batch(batch, monthly=True)
+            for key in ("monthly", "yearly", "flags"):
+                assert np.array_equal(got[key], want[key], equal_nan=True), (env, key)
+        for k in env:
+            monkeypatch.delenv(k)
