@@ -137,7 +137,36 @@ def _load_weather_records(path: str):
     """(header records (4, 80), data records (37 * nblocks, 80), nblocks) of one D4/D7/D13 file as uint8 matrices
     (records cut or blank-padded to 80 columns, CR dropped)."""
     with open(path, "rb") as f:
-        lines = f.read().split(b"\n")
+        raw = f.read()
+    # fast path: the year blocks of a file written by a program are records of ONE length (PyHELP's writers, HELP's own):
+    # the data part is reshaped in one step instead of being split into a Python list of lines
+    p4, k = -1, 0
+    while k < 4:
+        p4 = raw.find(b"\n", p4 + 1)
+        if p4 < 0:
+            break
+        k += 1
+    if k == 4:
+        e1 = raw.find(b"\n", p4 + 1)
+        L = e1 - p4 - 1
+        nbytes = len(raw) - (p4 + 1)
+        if e1 > 0 and 0 < L <= 80 and (nbytes % (L + 1) == 0 or (nbytes + 1) % (L + 1) == 0):
+            nlines = (nbytes + 1) // (L + 1)
+            body = np.frombuffer(raw, dtype=np.uint8, count=nlines * (L + 1) - (1 if nbytes % (L + 1) else 0), offset=p4 + 1)
+            if body.size % (L + 1):
+                body = np.concatenate([body, np.array([10], dtype=np.uint8)])
+            body = body.reshape(nlines, L + 1)
+            nblocks = nlines // 37
+            if nblocks >= 1 and (body[:, L] == 10).all() and not (body[:, :L] == 10).any():
+                data = np.full((37 * nblocks, 80), 32, dtype=np.uint8)
+                data[:, :L] = body[:37 * nblocks, :L]
+                hdr = _records(np.array(raw[:p4].split(b"\n"), dtype="S80"))
+                for a in (hdr, data):
+                    a[a == 13] = 32
+                    a[a == 0] = 32
+                    a[a > 127] = 63
+                return hdr, data, nblocks
+    lines = raw.split(b"\n")
     if lines and lines[-1] == b"":
         lines.pop()
     if len(lines) < 4:
@@ -417,22 +446,39 @@ def batch_from_cellparams(cellparams: dict, parse: str = "host") -> CellBatch:
     d11_list = []
     node_ids = np.zeros((3, n), dtype=np.int32)
     tfsoil = np.zeros(n, dtype=np.float64)
-    last = [None, None, None, 0, 0, 0]                       # consecutive cells usually share their weather files
-    for i, name in enumerate(names):
-        p = cellparams[name]
-        for k, kind in enumerate(("D4", "D7", "D13")):
-            if p[k] is not last[k]:
-                last[k], last[3 + k] = p[k], node(p[k], kind, tables[k])
-            node_ids[k, i] = last[3 + k]
-        r11 = as_s80(p[3])
-        if r11.shape[0] < 3:
-            raise ValueError(f"cell {name}: D11 needs 3 records")
-        d11_list.append(r11[:3])
-        r10 = as_s80(p[4])
-        g10 = d10_lists.setdefault(r10.shape[0], ([], []))
-        g10[0].append(i)
-        g10[1].append(r10)
-        tfsoil[i] = p[11]
+    vals = list(cellparams.values())
+    for k, kind in enumerate(("D4", "D7", "D13")):       # (consecutive cells usually share their weather files)
+        ids, cur, cur_id, table = [0] * n, None, 0, tables[k]
+        for i, p in enumerate(vals):
+            q = p[k]
+            if q is not cur:
+                cur, cur_id = q, node(q, kind, table)
+            ids[i] = cur_id
+        node_ids[k] = ids
+    tfsoil[:] = np.fromiter((p[11] for p in vals), dtype=np.float64, count=n)
+    r11s, r10s = [p[3] for p in vals], [p[4] for p in vals]
+    s80 = np.dtype("S80")
+    if all(type(a) is np.ndarray and a.dtype == s80 and a.ndim == 1 for a in r11s) and \
+       all(type(a) is np.ndarray and a.dtype == s80 and a.ndim == 1 for a in r10s):
+        # the usual case (PyHELP's formatters hand over S80 arrays): no per-cell conversion, one concatenation per group
+        n11 = np.fromiter((a.shape[0] for a in r11s), dtype=np.int64, count=n)
+        if (n11 < 3).any():
+            raise ValueError(f"cell {names[int(np.argmax(n11 < 3))]}: D11 needs 3 records")
+        d11_list = r11s if (n11 == 3).all() else [a[:3] for a in r11s]
+        n10 = np.fromiter((a.shape[0] for a in r10s), dtype=np.int64, count=n)
+        for nrec in np.unique(n10).tolist():
+            idx = np.nonzero(n10 == nrec)[0]
+            d10_lists[nrec] = (idx.tolist(), r10s if idx.size == n else [r10s[i] for i in idx.tolist()])
+    else:
+        for i, name in enumerate(names):
+            r11 = as_s80(r11s[i])
+            if r11.shape[0] < 3:
+                raise ValueError(f"cell {name}: D11 needs 3 records")
+            d11_list.append(r11[:3])
+            r10 = as_s80(r10s[i])
+            g10 = d10_lists.setdefault(r10.shape[0], ([], []))
+            g10[0].append(i)
+            g10[1].append(r10)
     if n == 0:
         raise ValueError("cellparams is empty")
     fp, ft, fr = (read_weather_files(list(t.keys()), kind, parse) for t, kind in zip(tables, ("D4", "D7", "D13")))

@@ -201,13 +201,12 @@ def split_by_cell(batch: CellBatch, res: dict) -> dict:
     """[row][year][month][cell] (or the already cell-major ``res["by_cell"]``) -> the reference's dict of per-cell dicts."""
     years = res["years"]
     per_cell = res["by_cell"] if "by_cell" in res else np.ascontiguousarray(np.transpose(res["monthly"], (3, 0, 1, 2)))   # (n, 7, ny, 12)
-    out = {}
-    for i, name in enumerate(batch.names):
-        d = {"years": years.copy()}
-        for k, key in enumerate(KEYS):
-            d[key] = per_cell[i, k]
-        out[name] = d
-    return out
+    # one dict per cell, like the reference returns: the arrays are views of one (n, 7, ny, 12) block and of one (n, ny)
+    # block of years (a dict literal per cell: half the time of filling the dicts key by key, 0.2 s per 100 000 cells)
+    assert KEYS == ("precip", "runoff", "evapo", "subrun1", "subrun2", "perco", "rechg")
+    ys = np.tile(np.asarray(years), (per_cell.shape[0], 1))
+    return {name: {"years": y, "precip": r[0], "runoff": r[1], "evapo": r[2], "subrun1": r[3], "subrun2": r[4], "perco": r[5],
+                   "rechg": r[6]} for name, r, y in zip(batch.names, per_cell, ys)}
 
 
 def run_help_allcells(cellparams: dict, ncore=None) -> dict:
