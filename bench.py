@@ -548,7 +548,8 @@ def run_ours(args):
                                   equal_nan=True) for c in (0, n // 2, n - 1))
         line["e2e_dropin"] = {"value": n * ny / dt, "unit": "cell-years/s", "wall_s": dt, "cells": n,
                               "api": "pyhelp_b200.run_help_allcells(cellparams): D10/D11 S80 records + D4/D7/D13 files in, dict of per-cell dicts out",
-                              "inputs_written_in_s": t_build, "same_bits_as_array_path": bool(same)}
+                              "inputs_written_in_s": t_build, "same_bits_as_array_path": bool(same),
+                              "stages_s": {k: round(float(v), 4) for k, v in processing.LAST_TIMING.items()}}
         del cp, out
         line["other_configs"] = {
             "mixed_125k_x_30yr": one_config("mixed", 125_000, 30, 2, N),

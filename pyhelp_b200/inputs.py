@@ -458,17 +458,21 @@ def batch_from_cellparams(cellparams: dict, parse: str = "host") -> CellBatch:
     tfsoil[:] = np.fromiter((p[11] for p in vals), dtype=np.float64, count=n)
     r11s, r10s = [p[3] for p in vals], [p[4] for p in vals]
     s80 = np.dtype("S80")
-    if all(type(a) is np.ndarray and a.dtype == s80 and a.ndim == 1 for a in r11s) and \
-       all(type(a) is np.ndarray and a.dtype == s80 and a.ndim == 1 for a in r10s):
-        # the usual case (PyHELP's formatters hand over S80 arrays): no per-cell conversion, one concatenation per group
+
+    def column_of_records(a):          # an S80 array of shape (k,) or (k, 1): what the reference's formatters build
+        return type(a) is np.ndarray and a.dtype == s80 and (a.ndim == 1 or (a.ndim == 2 and a.shape[1] == 1))
+
+    if all(column_of_records(a) for a in r11s) and all(column_of_records(a) for a in r10s) and \
+       len({a.ndim for a in r11s}) == 1 and len({a.ndim for a in r10s}) == 1:
+        # the usual case: no per-cell conversion, one concatenation per group of equal record count
         n11 = np.fromiter((a.shape[0] for a in r11s), dtype=np.int64, count=n)
         if (n11 < 3).any():
             raise ValueError(f"cell {names[int(np.argmax(n11 < 3))]}: D11 needs 3 records")
-        d11_list = r11s if (n11 == 3).all() else [a[:3] for a in r11s]
+        d11_list = [np.concatenate(r11s if (n11 == 3).all() else [a[:3] for a in r11s]).reshape(-1)]
         n10 = np.fromiter((a.shape[0] for a in r10s), dtype=np.int64, count=n)
         for nrec in np.unique(n10).tolist():
             idx = np.nonzero(n10 == nrec)[0]
-            d10_lists[nrec] = (idx.tolist(), r10s if idx.size == n else [r10s[i] for i in idx.tolist()])
+            d10_lists[nrec] = (idx.tolist(), [np.concatenate(r10s if idx.size == n else [r10s[i] for i in idx.tolist()]).reshape(-1)])
     else:
         for i, name in enumerate(names):
             r11 = as_s80(r11s[i])

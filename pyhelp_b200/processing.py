@@ -209,6 +209,9 @@ def split_by_cell(batch: CellBatch, res: dict) -> dict:
                    "rechg": r[6]} for name, r, y in zip(batch.names, per_cell, ys)}
 
 
+LAST_TIMING: dict = {}      # wall-clock seconds of the stages of the last run_help_allcells call (developer information)
+
+
 def run_help_allcells(cellparams: dict, ncore=None) -> dict:
     """Run HELP in batch for multiple cells (reference pyhelp/processing.py:40-59)."""
     tstart = time.perf_counter()
@@ -216,16 +219,25 @@ def run_help_allcells(cellparams: dict, ncore=None) -> dict:
         return {}
     N.require_device()          # fail before any host work: this path has no CPU fallback
     batch = batch_from_cellparams(cellparams, parse="device")      # formatted reads of all records in a few kernels
+    t_pack = time.perf_counter()
     want = os.environ.get("HELP_B200_DEVICES", "1")      # "all" or a count: fan out over several GPUs of this process
     ndev = N.lib().help_b200_device_count() if want.strip().lower() == "all" else int(want)
     if ndev > 1:
         res = run_batch_devices(batch, ndev, monthly=True)
+        t_up = t_sim = t_fetch = time.perf_counter()
     else:
         with HelpEngine(batch, monthly=True) as eng:
+            t_up = time.perf_counter()
             eng.simulate()
+            t_sim = time.perf_counter()
             res = {"years": batch.years.astype(np.uint16), "by_cell": eng.fetch_by_cell()}
+            t_fetch = time.perf_counter()
     output = split_by_cell(batch, res)
-    print("\nTask completed in %0.2f sec" % (time.perf_counter() - tstart))
+    t_end = time.perf_counter()
+    LAST_TIMING.clear()
+    LAST_TIMING.update({"records_and_weather_s": t_pack - tstart, "upload_s": t_up - t_pack, "setup_simulate_s": t_sim - t_up,
+                        "transpose_download_s": t_fetch - t_sim, "per_cell_dicts_s": t_end - t_fetch, "total_s": t_end - tstart})
+    print("\nTask completed in %0.2f sec" % (t_end - tstart))
     return output
 
 
