@@ -107,6 +107,17 @@ def test_fixed_length_records_fast_path_equals_the_padded_path(tmp_path):
     g.write_bytes(b"\r\n".join(txt))
     b = inputs.read_weather_file(str(g), "D7")
     assert np.array_equal(a.data, b.data) and np.array_equal(a.years, b.years) and a.units == b.units
+    # the year blocks of a written file are records of one length and are reshaped in one step; a file whose lines differ
+    # in length (hand-edited: trailing blanks stripped, an extra line, no final newline) goes the line-by-line way -- the
+    # same records either way
+    raw = open(f, "rb").read()
+    lines = raw.split(b"\n")
+    ragged = b"\n".join(x.rstrip() if k % 3 else x for k, x in enumerate(lines))
+    for k, variant in enumerate((raw.rstrip(b"\n"), raw + b"one more line\n", ragged, raw.replace(b"\n", b"\r\n"))):
+        h = tmp_path / f"variant{k}.D7"
+        h.write_bytes(variant)
+        c = inputs.read_weather_file(str(h), "D7")
+        assert np.array_equal(a.data, c.data) and np.array_equal(a.years, c.years) and np.array_equal(a.header12, c.header12), k
 
 
 def test_idfs_prescan_reads_f61_whatever_the_units(tmp_path):
