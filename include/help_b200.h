@@ -204,6 +204,21 @@ int help_b200_nearest_nodes(int64_t n_cells, const double* cell_lat, const doubl
 int help_b200_pack_weather(const double* table, int64_t n_days, int32_t n_nodes, const int32_t* year_day0,
                            const int32_t* year_ndays, int32_t n_years, int32_t decimals, float* out);
 
+/* The same, but the packed table stays in device memory: *out_dev receives a device pointer that may be given as
+ * help_b200_batch.pre / .tmp / .rad of any number of engines on the same device (help_b200_engine_create copies it device to
+ * device and converts its own copy) and is released with help_b200_device_free.  Saves the device -> host -> device round trip
+ * of n_nodes x n_years x 368 x 4 bytes per table between packing and simulating.                                              */
+int help_b200_pack_weather_resident(const double* table, int64_t n_days, int32_t n_nodes, const int32_t* year_day0,
+                                    const int32_t* year_ndays, int32_t n_years, int32_t decimals, float** out_dev);
+
+/* READIN's pre-scan of the radiation file for IDFS (pyhelp/HELP3O.FOR:1348-1375) on a device-resident radiation table
+ * rad_dev[n_nodes][n_years][HELP_B200_DAYS] (raw file values: MJ/m2 with iu13 = 2, langleys with 1): out[n_nodes][2] (host) =
+ * IDFS for a northern / southern site -- help_b200_batch.idfs.                                                                 */
+int help_b200_idfs_prescan_resident(const float* rad_dev, int32_t n_nodes, int32_t n_years, int32_t iu13, int32_t* out);
+
+/* Release a device buffer handed out by this library (help_b200_pack_weather_resident).  NULL is ignored.                      */
+void help_b200_device_free(void* p);
+
 /* Fortran formatted READ of fixed-width numeric fields for a whole matrix of records (8f row 1):
  * the reads READCD (pyhelp/HELP3O.FOR:1100-1129, FORMAT(I10,10F5.2) / (I5,10F6.1)) and READIN (HELP3O.FOR:1221-1225 D11,
  * :1260-1300 D10) do per cell, done once for all records of a drop-in run_help_allcells(cellparams) call

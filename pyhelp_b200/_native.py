@@ -107,6 +107,13 @@ def lib():
     L.help_b200_nearest_nodes.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     L.help_b200_pack_weather.restype = C.c_int
     L.help_b200_pack_weather.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
+    L.help_b200_pack_weather_resident.restype = C.c_int
+    L.help_b200_pack_weather_resident.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
+                                                  C.POINTER(C.c_void_p)]
+    L.help_b200_idfs_prescan_resident.restype = C.c_int
+    L.help_b200_idfs_prescan_resident.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
+    L.help_b200_device_free.restype = None
+    L.help_b200_device_free.argtypes = [C.c_void_p]
     L.help_b200_parse_fields.restype = C.c_int
     L.help_b200_parse_fields.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
     L.help_b200_engine_fetch_monthly_by_cell.restype = C.c_int
@@ -134,3 +141,23 @@ def set_device(index: int):
 
 def ptr(a: np.ndarray | None):
     return None if a is None else a.ctypes.data
+
+
+class DeviceTable:
+    """A float32 table that lives in device memory (``help_b200_pack_weather_resident``): what ``CellBatch.pre/tmp/rad`` may
+    hold instead of a numpy array.  It has a shape and a size but no host values; the buffer is released with the object."""
+
+    def __init__(self, dev_ptr: int, shape):
+        self.ptr = int(dev_ptr)
+        self.shape = tuple(int(x) for x in shape)
+        self.dtype = np.dtype(np.float32)
+
+    @property
+    def nbytes(self) -> int:
+        return int(np.prod(self.shape)) * 4
+
+    def __del__(self):
+        p, self.ptr = getattr(self, "ptr", 0), 0
+        if p and _lib is not None:
+            _lib.help_b200_device_free(p)
+

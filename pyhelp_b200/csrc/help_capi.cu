@@ -250,9 +250,13 @@ extern "C" int help_b200_engine_create(const help_b200_batch* b, int want_monthl
   CUB_(cudaEventRecord(e->ev[0], st));
 #define H2D(dst, src, count) CUB_(cudaMemcpyAsync(dst, src, (size_t)(count) * sizeof(*(dst)), cudaMemcpyHostToDevice, st))
   H2D(e->d_years, b->years, ny);
-  H2D(e->d_pre, b->pre, (size_t)b->n_nodes_p * wrow);
-  H2D(e->d_tmp, b->tmp, (size_t)b->n_nodes_t * wrow);
-  H2D(e->d_rad, b->rad, (size_t)b->n_nodes_r * wrow);
+  // (the weather tables may already be on this device -- help_b200_pack_weather_resident: the copy direction is
+  // taken from the pointer; the engine converts its own copy to the reference's internal units in place)
+#define ANY2D(dst, src, count) CUB_(cudaMemcpyAsync(dst, src, (size_t)(count) * sizeof(*(dst)), cudaMemcpyDefault, st))
+  ANY2D(e->d_pre, b->pre, (size_t)b->n_nodes_p * wrow);
+  ANY2D(e->d_tmp, b->tmp, (size_t)b->n_nodes_t * wrow);
+  ANY2D(e->d_rad, b->rad, (size_t)b->n_nodes_r * wrow);
+#undef ANY2D
   H2D(e->d_tm, b->tm_normals, (size_t)b->n_nodes_t * 12);
   H2D(e->d_iu4, b->iu4, b->n_nodes_p); H2D(e->d_iu7, b->iu7, b->n_nodes_t); H2D(e->d_iu13, b->iu13, b->n_nodes_r);
   H2D(e->d_idfs, b->idfs, (size_t)b->n_nodes_r * 2);
@@ -668,9 +672,10 @@ extern "C" int help_b200_nearest_nodes(int64_t n_cells, const double* cell_lat, 
   return done(0);
 }
 
-extern "C" int help_b200_pack_weather(const double* table, int64_t n_days, int32_t n_nodes, const int32_t* year_day0,
-                                      const int32_t* year_ndays, int32_t n_years, int32_t decimals, float* out) {
-  if (!table || !year_day0 || !year_ndays || !out || n_days < 1 || n_nodes < 1 || n_years < 1 || decimals < 0 || decimals > 15)
+// pack_weather for both entry points: the packed table is copied to `out_host` and/or handed over in `*keep_dev`
+static int pack_weather_impl(const double* table, int64_t n_days, int32_t n_nodes, const int32_t* year_day0,
+                             const int32_t* year_ndays, int32_t n_years, int32_t decimals, float* out_host, float** keep_dev) {
+  if (!table || !year_day0 || !year_ndays || (!out_host && !keep_dev) || n_days < 1 || n_nodes < 1 || n_years < 1 || decimals < 0 || decimals > 15)
     return fail(HELP_B200_EINVAL, "pack_weather: bad argument");
   for (int y = 0; y < n_years; ++y)
     if (year_day0[y] < 0 || year_ndays[y] < 0 || year_ndays[y] > kDays || (int64_t)year_day0[y] + year_ndays[y] > n_days)
@@ -678,7 +683,12 @@ extern "C" int help_b200_pack_weather(const double* table, int64_t n_days, int32
   if (help_b200_device_count() < 1) return fail(HELP_B200_ENODEV, "no CUDA device (this engine has no CPU path)");
   double* d_tab = nullptr; float* d_out = nullptr; int32_t *d_d0 = nullptr, *d_nd = nullptr;
   int rc = 0;
-  auto done = [&](int code) { cudaDeviceSynchronize(); dev_free(d_tab); dev_free(d_out); dev_free(d_d0); dev_free(d_nd); return code; };
+  auto done = [&](int code) {
+    cudaDeviceSynchronize();
+    dev_free(d_tab); dev_free(d_d0); dev_free(d_nd);
+    if (code == 0 && keep_dev) *keep_dev = d_out; else dev_free(d_out);
+    return code;
+  };
   const size_t n_in = (size_t)n_days * n_nodes, n_out = (size_t)n_nodes * n_years * kDays;
   if ((rc = dev_alloc(&d_tab, n_in)) || (rc = dev_alloc(&d_out, n_out)) || (rc = dev_alloc(&d_d0, (size_t)n_years)) ||
       (rc = dev_alloc(&d_nd, (size_t)n_years)))
@@ -693,9 +703,42 @@ extern "C" int help_b200_pack_weather(const double* table, int64_t n_days, int32
     pack_weather_kernel<<<grid, dim3(32, 8)>>>(d_tab, (int64_t)n_nodes, d_d0, d_nd, n_years, S, d_out);
     ce = cudaGetLastError();
   }
-  if (ce == cudaSuccess) ce = cudaMemcpy(out, d_out, sizeof(float) * n_out, cudaMemcpyDeviceToHost);
+  if (ce == cudaSuccess && out_host) ce = cudaMemcpy(out_host, d_out, sizeof(float) * n_out, cudaMemcpyDeviceToHost);
   if (ce != cudaSuccess) return done(fail(HELP_B200_ECUDA, "pack_weather", ce));
   return done(0);
+}
+
+extern "C" int help_b200_pack_weather(const double* table, int64_t n_days, int32_t n_nodes, const int32_t* year_day0,
+                                      const int32_t* year_ndays, int32_t n_years, int32_t decimals, float* out) {
+  return pack_weather_impl(table, n_days, n_nodes, year_day0, year_ndays, n_years, decimals, out, nullptr);
+}
+
+extern "C" int help_b200_pack_weather_resident(const double* table, int64_t n_days, int32_t n_nodes, const int32_t* year_day0,
+                                               const int32_t* year_ndays, int32_t n_years, int32_t decimals, float** out_dev) {
+  if (!out_dev) return fail(HELP_B200_EINVAL, "pack_weather_resident: out_dev is NULL");
+  *out_dev = nullptr;
+  return pack_weather_impl(table, n_days, n_nodes, year_day0, year_ndays, n_years, decimals, nullptr, out_dev);
+}
+
+extern "C" int help_b200_idfs_prescan_resident(const float* rad_dev, int32_t n_nodes, int32_t n_years, int32_t iu13, int32_t* out) {
+  if (!rad_dev || !out || n_nodes < 1 || n_years < 1) return fail(HELP_B200_EINVAL, "idfs_prescan_resident: bad argument");
+  if (help_b200_device_count() < 1) return fail(HELP_B200_ENODEV, "no CUDA device (this engine has no CPU path)");
+  int32_t* d_out = nullptr;
+  int rc = dev_alloc(&d_out, (size_t)2 * n_nodes);
+  if (rc) return rc;
+  idfs_prescan_kernel<<<(unsigned)((2 * n_nodes + 127) / 128), 128>>>(rad_dev, n_nodes, n_years, iu13, d_out);
+  cudaError_t ce = cudaGetLastError();
+  if (ce == cudaSuccess) ce = cudaMemcpy(out, d_out, sizeof(int32_t) * 2 * n_nodes, cudaMemcpyDeviceToHost);
+  cudaDeviceSynchronize();
+  dev_free(d_out);
+  if (ce != cudaSuccess) return fail(HELP_B200_ECUDA, "idfs_prescan_resident", ce);
+  return 0;
+}
+
+extern "C" void help_b200_device_free(void* p) {
+  if (!p) return;
+  cudaDeviceSynchronize();
+  dev_free(p);
 }
 
 extern "C" int help_b200_parse_fields(const uint8_t* text, int64_t n_records, int32_t reclen, const int32_t* col,

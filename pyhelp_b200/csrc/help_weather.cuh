@@ -55,4 +55,24 @@ __global__ void pack_weather_kernel(const double* __restrict__ table, int64_t n_
   }
 }
 
+// READIN's pre-scan of the radiation file for the soil-thaw day count IDFS (pyhelp/HELP3O.FOR:1348-1375; host twin:
+// pyhelp_b200/grid.py idfs_prescan_nodes): REAL*4 sum, in file order, of the December (days 335-365, northern sites) and June
+// (days 152-182, southern sites) values of the first <= 100 years of rad[node][year][kDays]; one thread per node and
+// hemisphere (the sum is sequential by definition).  out[node][2].
+__global__ void idfs_prescan_kernel(const float* __restrict__ rad, int n_nodes, int n_years, int iu13, int32_t* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 2 * n_nodes) return;
+  const int node = i >> 1, h = i & 1;
+  const int lo = h ? 151 : 334;
+  const int nyrs = n_years < 100 ? n_years : 100;
+  const float* r = rad + (int64_t)node * n_years * kDays;
+  float radtot = 0.0f;
+  for (int y = 0; y < nyrs; ++y)
+    for (int d = lo; d < lo + 31; ++d) radtot = radtot + r[(int64_t)y * kDays + d];
+  float radavg = (nyrs > 1) ? (radtot / (float)nyrs) / 31.0f : radtot / 31.0f;
+  if (iu13 != 1) radavg = radavg * 23.89f;
+  int idfs = (int)(35.4f - (0.154f * radavg));
+  out[i] = idfs < 1 ? 1 : idfs;
+}
+
 }  // namespace helpb200

@@ -63,10 +63,20 @@ def weather_to_nodes(years_of_day: np.ndarray, values: np.ndarray, decimals: int
     file written by weather_reader.py (values quantised to `decimals`).  ``where="device"`` runs the
     format/read round trip and the transposition on the GPU (``help_b200_pack_weather``,
     ``csrc/help_weather.cuh``; same bits, tests/test_gpu_pack.py) -- the host version costs 0.4 s
-    per variable per 1000 nodes x 30 yr and is what a caller without a device at packing time uses."""
+    per variable per 1000 nodes x 30 yr and is what a caller without a device at packing time uses;
+    ``where="resident"`` does the same and leaves the result in device memory (a ``DeviceTable``: the
+    engine then copies it device to device instead of taking it through the host twice)."""
     years, day0, ndays = _year_blocks(years_of_day)
     values = np.asarray(values, dtype=np.float64)
     nn = values.shape[1]
+    if where == "resident":            # quantised and laid out on the GPU, and left there (N.DeviceTable)
+        import ctypes as C
+        tab = np.ascontiguousarray(values)
+        N.require_device()
+        dev = C.c_void_p()
+        N.check(N.lib().help_b200_pack_weather_resident(N.ptr(tab), tab.shape[0], nn, N.ptr(day0), N.ptr(ndays), years.size,
+                                                        int(decimals), C.byref(dev)), "pack_weather_resident")
+        return years, N.DeviceTable(dev.value, (nn, years.size, N.DAYS))
     out = np.zeros((nn, years.size, N.DAYS), dtype=F32)
     if where == "device":
         tab = np.ascontiguousarray(values)
@@ -75,7 +85,7 @@ def weather_to_nodes(years_of_day: np.ndarray, values: np.ndarray, decimals: int
                                                int(decimals), N.ptr(out)), "pack_weather")
         return years, out
     if where != "host":
-        raise ValueError("where must be 'host' or 'device'")
+        raise ValueError("where must be 'host', 'device' or 'resident'")
     q = quantize(values, decimals).astype(F32)
     for k in range(years.size):
         out[:, k, :ndays[k]] = q[day0[k]:day0[k] + ndays[k]].T
@@ -110,8 +120,8 @@ def batch_from_grid(grid: dict, years_of_day, precip, airtemp, solrad, node_p, n
     ``precip``/``airtemp``/``solrad``: [day][node] tables in mm, deg C, MJ/m2/day.
     ``extra_layers``: optional per-layer design fields PyHELP's formatter leaves blank
     (phole{i}, defec{i}, ipq{i}, trans{i}, recir{i}, layr{i}, subin{i}, sw{i}; per cell: ipre, osno) for landfill designs.
-    ``weather``: ``"host"`` or ``"device"`` -- where the weather tables are quantised and laid out
-    (:func:`weather_to_nodes`).
+    ``weather``: ``"host"``, ``"device"`` or ``"resident"`` -- where the weather tables are quantised and laid
+    out, and where they stay (:func:`weather_to_nodes`).
     Cells PyHELP would skip (nlayer == 0 or a -9999 layer field,
     preprocessing.py:32-35,150-153) must be removed by the caller (`runnable_cells`).
     """
@@ -183,7 +193,11 @@ def batch_from_grid(grid: dict, years_of_day, precip, airtemp, solrad, node_p, n
     _, tmp = weather_to_nodes(years_of_day, airtemp, 1, weather)
     _, rad = weather_to_nodes(years_of_day, solrad, 2, weather)
     npn, ntn, nrn = pre.shape[0], tmp.shape[0], rad.shape[0]
-    idfs = idfs_prescan_nodes(rad, 2)
+    if isinstance(rad, N.DeviceTable):
+        idfs = np.zeros((nrn, 2), dtype=np.int32)
+        N.check(N.lib().help_b200_idfs_prescan_resident(rad.ptr, nrn, int(years.size), 2, N.ptr(idfs)), "idfs_prescan_resident")
+    else:
+        idfs = idfs_prescan_nodes(rad, 2)
     names = [str(c) for c in g["cid"].tolist()] if "cid" in g else [str(i) for i in range(n)]
     return CellBatch(
         n, int(years.size), L, np.ascontiguousarray(years), pre, tmp, rad,

@@ -365,6 +365,10 @@ class CellBatch:
         for k in ("years", "pre", "tmp", "rad", "iu4", "iu7", "iu13", "tm_normals", "idfs",
                   "cell_f32", "cell_i32", "layer_f32", "layer_i32", "layer_rc"):
             a = getattr(self, k)
+            if isinstance(a, N.DeviceTable):          # weather packed on the device and left there (grid.weather_to_nodes)
+                assert k in ("pre", "tmp", "rad"), k
+                setattr(b, k, a.ptr)
+                continue
             assert a.flags["C_CONTIGUOUS"], k
             setattr(b, k, a.ctypes.data)
         return b

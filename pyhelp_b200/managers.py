@@ -179,7 +179,7 @@ class HelpManager:
             node[var] = _canonical_nodes(nearest, lat, lon, fext)
         batch = G.batch_from_grid(cols, years_of_day, self.precip_data.values, self.airtemp_data.values,
                                   self.solrad_data.values, node["precip"], node["airtemp"], node["solrad"],
-                                  tfsoil_c=tfsoil, sf_edepth=sf_edepth, sf_ulai=sf_ulai, sf_cn=sf_cn, weather="device")
+                                  tfsoil_c=tfsoil, sf_edepth=sf_edepth, sf_ulai=sf_ulai, sf_cn=sf_cn, weather="resident")
         context = np.asarray(cols["context"]).astype(np.int32)
         with processing.HelpEngine(batch, monthly=True) as eng:
             eng.simulate()

@@ -144,6 +144,8 @@ def compact_nodes(batch: CellBatch) -> CellBatch:
     """Drop the weather nodes no cell of this (sub-)batch references and renumber the rest, so a
     rank uploads ~W/world nodes instead of all W."""
     from . import _native as N
+    if any(isinstance(t, N.DeviceTable) for t in (batch.pre, batch.tmp, batch.rad)):
+        raise TypeError("compact_nodes needs the weather tables on the host (pack with weather='host' or 'device')")
     out = CellBatch(batch.n_cells, batch.n_years, batch.max_layers, batch.years, batch.pre, batch.tmp, batch.rad,
                     batch.iu4, batch.iu7, batch.iu13, batch.tm_normals, batch.idfs,
                     batch.cell_f32, batch.cell_i32.copy(), batch.layer_f32, batch.layer_i32, batch.layer_rc,

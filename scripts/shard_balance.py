@@ -26,7 +26,7 @@ for r, (a, b) in enumerate(ranges):
     used, inv = np.unique(node[idx], return_inverse=True)
     tabs = [np.ascontiguousarray(wx[k][:, used]) for k in ("precip", "airtemp", "solrad")]
     nloc = inv.astype(np.int32)
-    batch = G.batch_from_grid(sub, wx["years_of_day"], tabs[0], tabs[1], tabs[2], nloc, nloc, nloc, tfsoil_c=-3.0, weather="device")
+    batch = G.batch_from_grid(sub, wx["years_of_day"], tabs[0], tabs[1], tabs[2], nloc, nloc, nloc, tfsoil_c=-3.0, weather="resident")
     with processing.HelpEngine(batch, monthly=True) as eng:
         eng.simulate()
         ms.append(eng.ms_simulate)

@@ -52,6 +52,38 @@ def test_batch_from_grid_device_weather_gives_the_same_batch():
         assert np.array_equal(getattr(a, k), getattr(b, k)), k
 
 
+def test_resident_weather_gives_the_same_batch_and_the_same_results():
+    """weather='resident' (help_b200_pack_weather_resident: the packed tables stay in device memory, the engine copies them
+    device to device; IDFS from help_b200_idfs_prescan_resident) against weather='host': same IDFS, same simulation bits --
+    also when two engines are created from the one resident batch."""
+    from pyhelp_b200 import _native as N, processing
+    n, nn, ny = 96, 70, 3                                       # 70 nodes: ragged tiles; 2004 is a leap year
+    g = synth.grid_mixed(n, seed=2)
+    wx = synth.synth_weather(nn, 2003, ny, seed=5)
+    node = synth.assign_nodes(n, nn)
+    a = G.batch_from_grid(g, wx["years_of_day"], wx["precip"], wx["airtemp"], wx["solrad"], node, node, node, weather="host")
+    b = G.batch_from_grid(g, wx["years_of_day"], wx["precip"], wx["airtemp"], wx["solrad"], node, node, node, weather="resident")
+    assert all(isinstance(getattr(b, k), N.DeviceTable) and getattr(b, k).shape == getattr(a, k).shape for k in ("pre", "tmp", "rad"))
+    for k in ("years", "idfs", "cell_f32", "cell_i32", "layer_f32", "layer_i32", "layer_rc"):
+        assert np.array_equal(getattr(a, k), getattr(b, k)), k
+    assert b.nbytes() == a.nbytes()
+    want = processing.run_batch(a, monthly=True)
+    for _ in range(2):
+        got = processing.run_batch(b, monthly=True)
+        for key in ("monthly", "yearly", "flags"):
+            assert np.array_equal(got[key], want[key], equal_nan=True), key
+    sub = b.take(np.arange(0, n, 3))                             # a sub-batch shares the resident tables
+    assert np.array_equal(processing.run_batch(sub, monthly=False)["yearly"], want["yearly"][:, :, ::3])
+    # southern-hemisphere window and a single year: the pre-scan's other branches
+    idfs = np.zeros((nn, 2), dtype=np.int32)
+    _, rad1 = G.weather_to_nodes(wx["years_of_day"][:365], wx["solrad"][:365], 2, "resident")
+    N.check(N.lib().help_b200_idfs_prescan_resident(rad1.ptr, nn, 1, 2, N.ptr(idfs)), "idfs")
+    _, rad1h = G.weather_to_nodes(wx["years_of_day"][:365], wx["solrad"][:365], 2, "host")
+    assert np.array_equal(idfs, G.idfs_prescan_nodes(rad1h, 2))
+    N.check(N.lib().help_b200_idfs_prescan_resident(rad1.ptr, nn, 1, 1, N.ptr(idfs)), "idfs")
+    assert np.array_equal(idfs, G.idfs_prescan_nodes(rad1h, 1))
+
+
 def test_device_formatted_read_equals_host_read(tmp_path, rcra_dir):
     """help_b200_parse_fields (csrc/help_parse.cuh) vs the host's conversion of the same fixed-width fields: hand-made
     records with every form a Fortran input field takes, then the records and weather files of RCRA and of a synthetic
