@@ -86,7 +86,9 @@ typedef struct help_b200_batch {
   int32_t n_nodes_p, n_nodes_t, n_nodes_r;
   /* weather, one row per distinct input file ("node"); value [node][year][day],
    * day 0-based, row stride HELP_B200_DAYS floats, as READCD reads them
-   * (HELP3O.FOR:1100-1129), i.e. BEFORE the unit conversion of F:1138-1152.  */
+   * (HELP3O.FOR:1100-1129), i.e. BEFORE the unit conversion of F:1138-1152.
+   * pre / tmp / rad may be host pointers or device pointers on the engine's device
+   * (help_b200_pack_weather_resident); every other member is a host pointer.   */
   const int32_t* years;   /* [n_years] calendar year of each block (leap = year%4==0, F:1048) */
   const float* pre;       /* [n_nodes_p][n_years][HELP_B200_DAYS]             */
   const float* tmp;       /* [n_nodes_t][n_years][HELP_B200_DAYS]             */
