@@ -230,7 +230,7 @@ def test_launch_plan_does_not_change_a_bit(monkeypatch):
     """The launch plan of help_sim_kernel (help_capi.cu: register budget by batch size, block size by profile class,
     blocks in descending cost order) decides which SM simulates a cell and with whom it shares its day barrier, never
     what the cell computes: every override gives the bits of the default plan (which the families above hold to the oracle)."""
-    n, nn, ny = 700, 7, 2
+    n, nn, ny = 5000, 7, 2                                    # 157 blocks of 32: a second, partial round on 148 SMs
     g = synth.grid_mixed(n, seed=4)
     wx = synth.synth_weather(nn, 2003, ny, seed=6)
     node = synth.assign_nodes(n, nn)
@@ -241,7 +241,8 @@ def test_launch_plan_does_not_change_a_bit(monkeypatch):
                               node, node, node, tfsoil_c=-3.0)
     ref_plain = processing.run_batch(plain, monthly=True)
     for env in ({"HELP_B200_BLOCK": "32"}, {"HELP_B200_BLOCK": "512"}, {"HELP_B200_BLOCK": "96", "HELP_B200_SHAPE": "3"},
-                {"HELP_B200_SHAPE": "0"}, {"HELP_B200_SHAPE": "1"}, {"HELP_B200_SORT": "0"}, {"HELP_B200_PLAN": "1"}):
+                {"HELP_B200_SHAPE": "0"}, {"HELP_B200_SHAPE": "1"}, {"HELP_B200_SORT": "0"}, {"HELP_B200_PLAN": "1"},
+                {"HELP_B200_BALANCE": "1"}, {"HELP_B200_BLOCK": "64", "HELP_B200_BALANCE": "1"}):
         for k, v in env.items():
             monkeypatch.setenv(k, v)
         for batch, want in ((b, ref), (plain, ref_plain)):
