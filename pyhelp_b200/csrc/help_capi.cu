@@ -334,20 +334,9 @@ static int pick_block(int64_t n, int cap, int kind, int device) {
 
 // CAP = threads per SM the register budget keeps resident = the largest block the instantiation accepts.
 template <int MAXSEG, int CAP, int REGS>
-static void launch_sim(SimArgs A, cudaStream_t st, int kind, int device) {
+static void launch_sim(const SimArgs& A, cudaStream_t st, int kind, int device) {
   const int block = pick_block(A.count, CAP, kind, device);
-  const int64_t grid = (A.count + block - 1) / block;
-  // a launch that is resident at once: even out the SMs (help_sim.cuh); HELP_B200_BALANCE=1 switches it on (A/B pending: the default is the plain descending order)
-  A.bal_sms = A.bal_heavy = A.bal_rounds = 0;
-  int sms = 148, per_sm = 0;
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-  const char* f = getenv("HELP_B200_BALANCE");
-  if ((f && f[0] == '1') &&
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, help_sim_kernel<MAXSEG, CAP, REGS>, block, 0) == cudaSuccess &&
-      grid > sms && grid <= (int64_t)sms * per_sm && grid % sms != 0) {
-    A.bal_sms = sms; A.bal_rounds = (int)((grid + sms - 1) / sms); A.bal_heavy = (int)(grid - (int64_t)(A.bal_rounds - 1) * sms);
-  }
-  help_sim_kernel<MAXSEG, CAP, REGS><<<(unsigned)grid, block, 0, st>>>(A);
+  help_sim_kernel<MAXSEG, CAP, REGS><<<(unsigned)((A.count + block - 1) / block), block, 0, st>>>(A);
 }
 
 // One launch of image slots [A.first, A.first + A.count) with the instantiation for `maxseg_t` segments;

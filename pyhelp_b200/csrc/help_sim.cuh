@@ -52,7 +52,6 @@ struct SimArgs {
   int n_years;
   int64_t n_cells;        // cells of the batch (stride of the result arrays)
   int64_t first, count;   // image slots [first, first + count) are simulated by this launch
-  int bal_sms, bal_heavy, bal_rounds;   // single-wave launches: block placement that evens out the load of the SMs (0 = off)
   const int32_t* perm;    // image slot -> caller's cell index (NULL = identity)
   float* monthly;         // [7][ny][12][n] or NULL
   float* yearly;          // [5][ny][n] or NULL
@@ -599,22 +598,14 @@ __global__ void __launch_bounds__(CAP) __maxnreg__(REGS) help_sim_kernel(SimArgs
   // block the same number of times.  A thread past the end of the batch, or one whose cell cannot
   // be simulated, reads the last cell's constants (valid addresses) and sits out every day
   // (`live == false`); it only keeps the barrier count.
-  // Which cells a block simulates.  The sort key ascends with the cost of a cell, and the hardware hands blocks out in index
-  // order, breadth first over the SMs.  (1) A launch with more blocks than the GPU keeps resident runs the most expensive
-  // blocks first, so that the cheapest ones form its tail.  (2) A launch that is resident at once (782 blocks on 148 SMs:
-  // 42 SMs hold six blocks, 106 hold five) ends when its fullest SMs end: the SMs that receive a block in the last, partial
-  // round get the cheapest blocks in EVERY round, the others the expensive ones -- block b and block b + #SMs share an SM.
-  // Measured on B200 (profiles/r2_notes.md): (1) natural -5.2 %, mixed -8.6 %.
-  int64_t lblock;                                   // 0 = the cheapest cells of the launch
-  if (A.bal_rounds > 0) {
-    const int S = A.bal_sms, H = A.bal_heavy, R = A.bal_rounds;
-    const int r = (int)(blockIdx.x / (unsigned)S), q = (int)(blockIdx.x % (unsigned)S);
-    lblock = (q < H) ? (int64_t)H * R - 1 - ((int64_t)r * H + q)
-                     : (int64_t)gridDim.x - 1 - ((int64_t)r * (S - H) + (q - H));
-  } else {
-    lblock = (int64_t)gridDim.x - 1 - blockIdx.x;
-  }
-  const int64_t s_raw = lblock * blockDim.x + threadIdx.x;
+#ifndef HELP_FWD_BLOCKS
+  // The sort key ascends with the cost of a cell and the hardware hands out blocks in index order: the last blocks -- the ones
+  // that land on SMs which already hold a full share, and the tail of a launch with more blocks than the GPU keeps resident --
+  // must be the cheapest.  Measured on B200: 100 000 natural cells 5.2 % faster, 125 000 mixed cells 8.6 % (profiles/r2_notes.md).
+  const int64_t s_raw = (int64_t)(gridDim.x - 1 - blockIdx.x) * blockDim.x + threadIdx.x;
+#else
+  const int64_t s_raw = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+#endif
   bool live = s_raw < A.count;
   const int64_t s = A.first + (live ? s_raw : A.count - 1);
   const Image& img = A.img;

@@ -241,8 +241,7 @@ def test_launch_plan_does_not_change_a_bit(monkeypatch):
                               node, node, node, tfsoil_c=-3.0)
     ref_plain = processing.run_batch(plain, monthly=True)
     for env in ({"HELP_B200_BLOCK": "32"}, {"HELP_B200_BLOCK": "512"}, {"HELP_B200_BLOCK": "96", "HELP_B200_SHAPE": "3"},
-                {"HELP_B200_SHAPE": "0"}, {"HELP_B200_SHAPE": "1"}, {"HELP_B200_SORT": "0"}, {"HELP_B200_PLAN": "1"},
-                {"HELP_B200_BALANCE": "1"}, {"HELP_B200_BLOCK": "64", "HELP_B200_BALANCE": "1"}):
+                {"HELP_B200_SHAPE": "0"}, {"HELP_B200_SHAPE": "1"}, {"HELP_B200_SORT": "0"}, {"HELP_B200_PLAN": "1"}):
         for k, v in env.items():
             monkeypatch.setenv(k, v)
         for batch, want in ((b, ref), (plain, ref_plain)):
