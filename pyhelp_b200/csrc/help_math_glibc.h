@@ -229,6 +229,17 @@ HM_FN int g_checkint(uint64_t iy) {                        // 0: not an integer,
 
 // pow outside the straight-line case: x not a positive normal, or |y| outside [2^-65, 2^63)
 HM_NOINLINE double g_pow_special(double x, double y) {
+  // NaN operands first, with floating-point tests: 1 for y == 0 or x == 1, else the library's NaN (x + y; x * x with the
+  // sign of x**y for a finite y) -- what the integer tests below return for them.  A cell with inconsistent soil constants
+  // carries NaN through every power of every sub-step, and a launch waits for its slowest warp (profiles/r2_notes.md).
+  if (x != x || y != y) {
+    if (y == 0.0) return 1.0;
+    if (x == 1.0) return 1.0;
+    if (y != y || (hi32(y) & 0x7fffffffu) == 0x7ff00000u) return hm_add(x, y);
+    double x2 = hm_mul(x, x);
+    if ((hi32(x) >> 31) && g_checkint(as_u64(y)) == 1) x2 = -x2;
+    return x2;
+  }
   uint64_t ix = as_u64(x);
   const uint64_t iy = as_u64(y);
   uint32_t topx = (uint32_t)(ix >> 52);

@@ -132,6 +132,10 @@ def test_special_values():
     assert np.isnan(ev("pow", [-2.0], [0.5])[0]) and ev("pow", [-2.0], [3.0])[0] == -8.0
     assert np.isinf(ev("pow", [0.0], [-1.0])[0]) and ev("pow", [1e-310], [2.0])[0] == 0.0
     assert ev("exp", [0.0, 800.0, -800.0]).tolist() == [1.0, np.inf, 0.0]
+    # NaN operands return early from the special-case routine: the library's results
+    nan = float("nan")
+    got = ev("pow", [nan, nan, nan, nan, 1.0, 2.0, -1.0, nan, -nan], [3.0, 2.5, 0.0, -0.0, nan, nan, nan, np.inf, 3.0])
+    assert np.isnan(got[[0, 1, 5, 6, 7, 8]]).all() and (got[[2, 3, 4]] == 1.0).all()
     assert ev("log", [1.0])[0] == 0.0 and np.isnan(ev("log", [-1.0])[0]) and ev("log", [0.0])[0] == -np.inf
     assert ev("sin", [0.0])[0] == 0.0 and ev("cos", [0.0])[0] == 1.0 and ev("atan", [0.0])[0] == 0.0
 
